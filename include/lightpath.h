@@ -1,0 +1,239 @@
+/*
+ * lightpath.h — C ABI of liblightpath.so, the B200 (sm_100a) implementation of
+ * the per-pixel Schwarzschild null-geodesic ray-tracing hot path of
+ * dhg14n9/Light-path-tracer.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / C++ types.
+ * Every entry point cites the reference interface it replaces (file:line into
+ * the reference tree).  Conventions:
+ *
+ *   - every function returns an int: LP_OK (0) or a negative LP_ERR_* code;
+ *     nothing throws, nothing prints;
+ *   - all array pointers are DEVICE pointers owned by the caller unless the
+ *     parameter name starts with `h_` (host); the library never allocates or
+ *     frees device memory and keeps no mutable global state, so calls are
+ *     re-entrant and may be issued from several host threads / processes,
+ *     one or more per GPU;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = the
+ *     legacy default stream) and the call returns without synchronising;
+ *   - per-ray failures are reported the way the reference does it: integer
+ *     status (1 escaped, -1 captured, 0 invalid) and NaN in `final_alpha`
+ *     (metrics.py:69, :124-125, :667), never through the return code.
+ *
+ * There is no CPU fallback: on a machine without a usable CUDA device every
+ * compute entry point returns LP_ERR_CUDA.
+ */
+#ifndef LIGHTPATH_H_
+#define LIGHTPATH_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LP_ABI_VERSION 1
+
+/* ---- return codes ------------------------------------------------------- */
+#define LP_OK               0
+#define LP_ERR_INVALID_ARG (-1)   /* null pointer, negative size, bad enum      */
+#define LP_ERR_CUDA        (-2)   /* a CUDA runtime call / launch failed        */
+#define LP_ERR_UNSUPPORTED (-3)   /* legal request this build cannot serve      */
+
+/* ---- flags for the tracer entry points ---------------------------------- */
+#define LP_TRACE_STRICT     0u    /* default: every fp64 op separately rounded, in the
+                                     reference's order (bit-identical u, w, phi)   */
+#define LP_TRACE_FUSED      1u    /* allow FMA contraction inside the RK4 step
+                                     (faster, ulp-level different trajectories)     */
+#define LP_TRACE_NO_REPACK  2u    /* disable the two-phase long-ray re-packing      */
+
+/* ---- ray status codes (metrics.py:69, :125) ------------------------------ */
+#define LP_RAY_ESCAPED    1
+#define LP_RAY_CAPTURED (-1)
+#define LP_RAY_INVALID    0
+
+/* ---- source image element types for lp_remap ----------------------------- */
+#define LP_DTYPE_U8   0
+#define LP_DTYPE_F32  1
+#define LP_DTYPE_F64  2
+
+/* ---- sampling modes for lp_remap ------------------------------------------ */
+#define LP_SAMPLE_NEAREST   0     /* np.rint nearest neighbour: what the reference does
+                                     (image_lens.py:367-375)                         */
+#define LP_SAMPLE_BILINEAR  1     /* opt-in extension (not in the reference)          */
+
+/* Pinhole camera + black-hole screen frame of one image.
+ * Replaces the per-call recomputation at image_lens.py:138-143 / :304-308:
+ *   fx = (W/2)/tan(hfov/2), fy = (H/2)/tan(vfov/2); (d, e_x, e_y) = _psi_frame(psi)
+ *   (image_lens.py:38-61).  Coordinates are (y, x); +x right, +y down, +z forward. */
+typedef struct lp_camera {
+    int32_t height, width;      /* full frame size in pixels                     */
+    double  fx, fy;             /* focal lengths in pixels                        */
+    double  d[3];               /* unit vector camera -> black hole               */
+    double  e_x[3], e_y[3];     /* tangent basis around d                          */
+} lp_camera;
+
+/* Per-frame reductions ("kernel 3"): the counts the reference
+ * obtains with np.count_nonzero / np.any over boolean masks (image_lens.py:319-337,
+ * :178) plus the step totals the roofline numerator needs.  Lives in DEVICE memory,
+ * zero-initialised by lp_frame_stats_reset, accumulated by the tracer kernels. */
+typedef struct lp_frame_stats {
+    uint64_t n_rays;
+    uint64_t n_escaped;          /* status == 1 (finite final_alpha)                */
+    uint64_t n_captured;         /* status == -1                                    */
+    uint64_t n_invalid;          /* status == 0                                     */
+    uint64_t n_winding;          /* escaped and float32(final_alpha) > float32(pi/2)
+                                    (image_lens.py:322, NEP-50 float32 compare)     */
+    uint64_t sum_steps;          /* RK4 steps actually integrated                    */
+    uint64_t sum_warp_steps;     /* sum over warps of 32 * (steps the warp ran):
+                                    lane efficiency = sum_steps / sum_warp_steps     */
+    uint32_t max_steps;
+    uint32_t max_winding;        /* max n_half_orbits over all rays (clipped to u16) */
+    double   min_final_alpha;    /* over escaped rays; +inf / 0.0 when there are none */
+    double   max_final_alpha;
+} lp_frame_stats;
+
+/* ---- library / device ---------------------------------------------------- */
+
+int         lp_abi_version(void);
+const char *lp_error_string(int code);
+/* Number of visible CUDA devices (0 without a GPU); never fails. */
+int         lp_device_count(void);
+/* SM count and SM clock (kHz) of the current device. */
+int         lp_device_props(int32_t *sm_count, int32_t *clock_khz);
+
+/* Host-side helper: fill an lp_camera exactly as image_lens.py:38-61, :138-139 do.
+ * psi_y = pitch up, psi_x = yaw right (radians).  Pure host arithmetic (libm). */
+int lp_camera_init(int32_t height, int32_t width, double hfov, double vfov,
+                   double psi_y, double psi_x, lp_camera *h_cam);
+
+/* ---- kernel (1a): Schwarzschild Binet-equation RK4 tracer ---------------- */
+
+/* Replaces Schwarzschild.trace_rays_batch / _trace_rays_batch_schwarzschild
+ * (metrics.py:831-833, :661-668):  for every i in [0, n)
+ *     out_fa[i] = final_alpha if the ray escapes else NaN
+ *     out_w[i]  = n_half_orbits (written for every status, metrics.py:668)
+ * with _schwarzschild_trace_ray_numba (metrics.py:120-145) semantics, fixed step
+ * h_max up to phi_max (the reference hard-codes 50.0 / 0.05 at metrics.py:833).
+ * out_status (int8: 1/-1/0) and out_steps (int32) are optional (NULL to skip).
+ * stats (device, optional) is accumulated into. */
+int lp_schw_trace_batch_f64(const double *alphas, int64_t n,
+                            double M, double R_S, double r_obs,
+                            double phi_max, double h_max,
+                            double *out_fa, int64_t *out_w,
+                            int8_t *out_status, int32_t *out_steps,
+                            lp_frame_stats *stats, uint32_t flags, void *stream);
+
+/* Replaces image_lens.precompute_final_alpha_lookup (image_lens.py:155-178) for a
+ * Schwarzschild metric: float32 alpha table in (widened to fp64 per ray,
+ * image_lens.py:157), float32 final_alpha (NaN unless escaped) and uint16
+ * clipped winding out (image_lens.py:176-177).  n = H*W; phi_max/h_max as above. */
+int lp_schw_trace_alpha32(const float *alpha32, int64_t n,
+                          double M, double R_S, double r_obs,
+                          double phi_max, double h_max,
+                          float *out_fa32, uint16_t *out_w16,
+                          int8_t *out_status, int32_t *out_steps,
+                          lp_frame_stats *stats, uint32_t flags, void *stream);
+
+/* Fused build_alpha_lookup + precompute_final_alpha_lookup for rows
+ * [row0, row0+rows) of the frame described by cam (image_lens.py:133-178 in one
+ * launch; row tiles are what multi-GPU sharding hands each rank).  Output
+ * pointers address the FIRST ROW OF THE TILE (rows*width elements each).
+ * out_alpha32 is optional.  The alpha value is rounded to float32 and widened
+ * again before tracing, exactly as the reference's two-stage pipeline does. */
+int lp_schw_trace_frame(const lp_camera *h_cam, int32_t row0, int32_t rows,
+                        double M, double R_S, double r_obs,
+                        double phi_max, double h_max,
+                        float *out_alpha32, float *out_fa32, uint16_t *out_w16,
+                        int8_t *out_status, int32_t *out_steps,
+                        lp_frame_stats *stats, uint32_t flags, void *stream);
+
+/* Replaces image_lens.build_alpha_lookup (image_lens.py:133-152) for rows
+ * [row0, row0+rows).  decimals < 0 means "no rounding" (decimals=None). */
+int lp_build_alpha_lookup(const lp_camera *h_cam, int32_t row0, int32_t rows,
+                          int32_t decimals, float *out_alpha32, void *stream);
+
+/* ---- kernel (2): deflection -> background remap --------------------------- */
+
+/* Replaces image_lens.render_lensed_image (image_lens.py:296-397) for output rows
+ * [row0, row0+rows).  src is the FULL source image [H, W, channels] (channels = 1
+ * for a 2-D image), element type src_dtype; out addresses the first row of the
+ * tile and has the same element type / channel count.  fa32 / w16 address the
+ * tile's first row too; w16 may be NULL (winding_lookup=None).  Captured/invalid
+ * pixels are written as 0, winding pixels as WINDING_COLORS[clip(w,0,4)]
+ * (luma for channels == 1), out-of-frame samples as magenta.  channels == 4 with
+ * winding pixels present raises in the reference (shape mismatch): here the
+ * colour is written to the first 3 channels and the 4th is left 0. */
+int lp_remap(const void *src, int32_t src_dtype, int32_t channels,
+             const lp_camera *h_cam, const float *fa32, const uint16_t *w16,
+             int32_t render_loop_around, int32_t sampling,
+             int32_t row0, int32_t rows, void *out, void *stream);
+
+/* Fully fused frame: pixel -> alpha(f32) -> trace -> fa(f32), w(u16) -> remap, one
+ * launch, nothing but the finished pixels (and optional lookups) written. */
+int lp_render_frame(const void *src, int32_t src_dtype, int32_t channels,
+                    const lp_camera *h_cam, int32_t row0, int32_t rows,
+                    double M, double R_S, double r_obs, double phi_max, double h_max,
+                    int32_t render_loop_around, int32_t sampling,
+                    void *out, float *out_fa32, uint16_t *out_w16,
+                    lp_frame_stats *stats, uint32_t flags, void *stream);
+
+/* ---- kernel (3): shadow classification and frame reductions --------------- */
+
+/* Replaces the pixel loop of black_hole_shadow.main (black_hole_shadow.py:30-37):
+ * image[i*height + j] = 0.0 if arccos(cos(ax_i)*cos(ay_j)) < alpha_crit else 1.0,
+ * ax_i = arctan(((i - width/2)/(width/2)) * tan(fov/2)) (black_hole_shadow.py:7-9).
+ * image is float64 [width][height] (indexed [x][y] like the reference).
+ * n_shadow (device uint64, optional) receives the number of 0.0 pixels. */
+int lp_shadow_classify(int32_t width, int32_t height, double fov, double alpha_crit,
+                       double *image, uint64_t *n_shadow, void *stream);
+
+int lp_frame_stats_reset(lp_frame_stats *stats, void *stream);
+/* Stand-alone reduction over finished lookups (np.count_nonzero / np.any of
+ * image_lens.py:319-337): status and steps are optional. */
+int lp_frame_stats_reduce(const float *fa32, const uint16_t *w16,
+                          const int8_t *status, const int32_t *steps, int64_t n,
+                          lp_frame_stats *stats, void *stream);
+
+/* ---- kernel (1b): generic 8-D Hamiltonian tracer (scipy RK45 semantics) ---- */
+
+/* Replaces geodesic_tracer.trace_ray / integrate_geodesic (geodesic_tracer.py:22-82)
+ * for a Schwarzschild metric, batched over viewing angles: initial conditions as
+ * metrics.py:794-809, RHS as metrics.py:763-790, Dormand-Prince 5(4) with scipy's
+ * step controller (rtol, atol, max_step, first-step selection), terminal events at
+ * r_stop_inner (falling) / r_stop_outer (rising) located on the quartic dense
+ * output, outcome = captured if r_final <= 1.1*r_stop_inner.
+ *   out_state  : [n][8] final state (t, r, theta, phi, p_t, p_r, p_theta, p_phi)
+ *   out_lambda : [n] final affine parameter
+ *   out_outcome: [n] 1 escaped / -1 captured / 0 invalid (initial_conditions -> None)
+ *   out_nsteps : [n][2] accepted steps, RHS evaluations (optional)
+ * r_stop_inner / r_stop_outer <= 0 select the reference's defaults
+ * (capture_radius() = 1.01 R_S, 2*r_obs). */
+int lp_schw_rk45_trace_batch(const double *alphas, int64_t n,
+                             double M, double R_S, double r_obs,
+                             double lambda_max, double rtol, double atol, double max_step,
+                             double r_stop_inner, double r_stop_outer,
+                             double *out_state, double *out_lambda,
+                             int8_t *out_outcome, int32_t *out_nsteps, void *stream);
+
+/* Single-ray variant that also records the accepted-step trajectory (what
+ * OdeResult.t / .y hold, geodesic_tracer.py:57-67): traj is [max_points][9]
+ * (lambda, state[8]); *n_points (device int32) receives the count. */
+int lp_schw_rk45_trace_path(double alpha, double M, double R_S, double r_obs,
+                            double lambda_max, double rtol, double atol, double max_step,
+                            double r_stop_inner, double r_stop_outer,
+                            double *traj, int32_t max_points, int32_t *n_points,
+                            int8_t *out_outcome, int32_t *out_nfev, void *stream);
+
+/* ---- measurement helpers --------------------------------------------------- */
+
+/* FP64 pipe micro-benchmark: every thread runs `iters` rounds of 8 independent
+ * dependent-chain DFMAs (16*iters flop per thread).  Used by bench.py to MEASURE the
+ * FP64 roofline denominator on the box (it is not in MEASURED_PEAKS.json).
+ * sink: device double[blocks*threads]. */
+int lp_bench_dfma(int32_t blocks, int32_t threads, int32_t iters, double *sink, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIGHTPATH_H_ */

@@ -1,0 +1,298 @@
+// lp_trace.cu — kernel (1a): one-thread-per-ray Schwarzschild Binet-equation RK4 tracer
+// (replaces metrics.py:49-145, :661-668 and the drivers at image_lens.py:133-178).
+//
+// Layout: persistent grid (resident CTAs x SM count), each CTA walks 256-ray chunks
+// round-robin, a warp owns 32 consecutive rays (= 32 consecutive pixels of a row), so
+// the alpha loads and the fa / winding stores are fully coalesced.  The ray state
+// (u, w, step index) lives in registers in fp64; the per-configuration constants and the
+// strided phi table arrive through the kernel parameter (constant) bank.
+#include "lp_internal.cuh"
+#include "lp_remap.cuh"
+
+#define LP_TRACE_BLOCK 256
+
+enum { SRC_F64 = 0, SRC_F32 = 1, SRC_CAM = 2 };
+
+struct TraceArgs {
+    const void *alphas;     // SRC_F64: const double*, SRC_F32: const float*, SRC_CAM: unused
+    long long n;            // rays in this launch
+    void *out_fa;           // WIDE: double*, else float*
+    void *out_w;            // WIDE: int64_t*, else uint16_t*
+    float *out_alpha32;     // SRC_CAM only, optional
+    int8_t *out_status;     // optional
+    int32_t *out_steps;     // optional
+    lp_frame_stats *stats;  // optional
+    int32_t row0;           // SRC_CAM: first frame row of the tile
+};
+
+template <bool FUSED, int SRC, bool WIDE>
+__global__ void __launch_bounds__(LP_TRACE_BLOCK)
+lp_trace_kernel(const TraceArgs a, const BinetConsts c, const CamConsts cam)
+{
+    StatAcc acc;
+    acc.init();
+    unsigned long long n_mine = 0;
+    const long long stride = (long long)gridDim.x * LP_TRACE_BLOCK;
+    for (long long base = (long long)blockIdx.x * LP_TRACE_BLOCK; base < a.n; base += stride) {
+        const long long i = base + threadIdx.x;
+        const bool live = i < a.n;
+        RayResult r;
+        r.status = 0; r.steps = 0; r.nh = 0; r.fa = 0.0;
+        if (live) {
+            double alpha;
+            if (SRC == SRC_F64) {
+                alpha = __ldg((const double *)a.alphas + i);
+            } else if (SRC == SRC_F32) {
+                alpha = (double)__ldg((const float *)a.alphas + i);   // image_lens.py:157
+            } else {
+                const int row = a.row0 + (int)(i / cam.width);
+                const int col = (int)(i % cam.width);
+                const double xc = cam_coord(col, cam.half_w, cam.fx);
+                const double yc = cam_coord(row, cam.half_h, cam.fy);
+                const float a32 = (float)pixel_alpha64(cam, xc, yc);     // image_lens.py:152
+                if (a.out_alpha32) a.out_alpha32[i] = a32;
+                alpha = (double)a32;
+            }
+            binet_trace<FUSED>(c, alpha, r);
+            const double fa = (r.status == 1) ? r.fa : __longlong_as_double(0x7ff8000000000000LL);
+            if (WIDE) {
+                ((double *)a.out_fa)[i] = fa;                          // metrics.py:667
+                ((long long *)a.out_w)[i] = r.nh;                      // metrics.py:668
+            } else {
+                ((float *)a.out_fa)[i] = (float)fa;                    // image_lens.py:176
+                const long long nh = r.nh < 0 ? 0 : (r.nh > 65535 ? 65535 : r.nh);
+                ((unsigned short *)a.out_w)[i] = (unsigned short)nh;   // image_lens.py:177
+            }
+            if (a.out_status) a.out_status[i] = (int8_t)r.status;
+            if (a.out_steps) a.out_steps[i] = r.steps;
+            n_mine++;
+        }
+        if (a.stats) acc.add(r, live);
+    }
+    if (a.stats) lp_stats_flush(acc, n_mine, a.stats);
+}
+
+template <int SRC, bool WIDE>
+static int launch_trace(const TraceArgs &a, const BinetConsts &c, const CamConsts &cam,
+                        uint32_t flags, cudaStream_t stream)
+{
+    if (a.n == 0) return LP_OK;
+    const bool fused = (flags & LP_TRACE_FUSED) != 0;
+    const void *fn = fused ? (const void *)lp_trace_kernel<true, SRC, WIDE>
+                           : (const void *)lp_trace_kernel<false, SRC, WIDE>;
+    int grid = 0;
+    int rc = lp_grid_for(fn, LP_TRACE_BLOCK, &grid);
+    if (rc != LP_OK) return rc;
+    const long long chunks = (a.n + LP_TRACE_BLOCK - 1) / LP_TRACE_BLOCK;
+    if (chunks < grid) grid = (int)chunks;
+    if (fused) lp_trace_kernel<true, SRC, WIDE><<<grid, LP_TRACE_BLOCK, 0, stream>>>(a, c, cam);
+    else       lp_trace_kernel<false, SRC, WIDE><<<grid, LP_TRACE_BLOCK, 0, stream>>>(a, c, cam);
+    return lp_check_launch();
+}
+
+extern "C" int lp_schw_trace_batch_f64(const double *alphas, int64_t n,
+                                       double M, double R_S, double r_obs,
+                                       double phi_max, double h_max,
+                                       double *out_fa, int64_t *out_w,
+                                       int8_t *out_status, int32_t *out_steps,
+                                       lp_frame_stats *stats, uint32_t flags, void *stream)
+{
+    if (n < 0) return LP_ERR_INVALID_ARG;
+    if (n > 0 && (!alphas || !out_fa || !out_w)) return LP_ERR_INVALID_ARG;
+    BinetConsts c;
+    int rc = lp_make_binet_consts(M, R_S, r_obs, phi_max, h_max, &c);
+    if (rc != LP_OK) return rc;
+    CamConsts cam = {};
+    TraceArgs a = {};
+    a.alphas = alphas; a.n = n; a.out_fa = out_fa; a.out_w = out_w;
+    a.out_status = out_status; a.out_steps = out_steps; a.stats = stats;
+    return launch_trace<SRC_F64, true>(a, c, cam, flags, (cudaStream_t)stream);
+}
+
+extern "C" int lp_schw_trace_alpha32(const float *alpha32, int64_t n,
+                                     double M, double R_S, double r_obs,
+                                     double phi_max, double h_max,
+                                     float *out_fa32, uint16_t *out_w16,
+                                     int8_t *out_status, int32_t *out_steps,
+                                     lp_frame_stats *stats, uint32_t flags, void *stream)
+{
+    if (n < 0) return LP_ERR_INVALID_ARG;
+    if (n > 0 && (!alpha32 || !out_fa32 || !out_w16)) return LP_ERR_INVALID_ARG;
+    BinetConsts c;
+    int rc = lp_make_binet_consts(M, R_S, r_obs, phi_max, h_max, &c);
+    if (rc != LP_OK) return rc;
+    CamConsts cam = {};
+    TraceArgs a = {};
+    a.alphas = alpha32; a.n = n; a.out_fa = out_fa32; a.out_w = out_w16;
+    a.out_status = out_status; a.out_steps = out_steps; a.stats = stats;
+    return launch_trace<SRC_F32, false>(a, c, cam, flags, (cudaStream_t)stream);
+}
+
+extern "C" int lp_schw_trace_frame(const lp_camera *h_cam, int32_t row0, int32_t rows,
+                                   double M, double R_S, double r_obs,
+                                   double phi_max, double h_max,
+                                   float *out_alpha32, float *out_fa32, uint16_t *out_w16,
+                                   int8_t *out_status, int32_t *out_steps,
+                                   lp_frame_stats *stats, uint32_t flags, void *stream)
+{
+    CamConsts cam;
+    int rc = lp_make_cam_consts(h_cam, &cam);
+    if (rc != LP_OK) return rc;
+    if (row0 < 0 || rows < 0 || (long long)row0 + rows > cam.height) return LP_ERR_INVALID_ARG;
+    const long long n = (long long)rows * cam.width;
+    if (n > 0 && (!out_fa32 || !out_w16)) return LP_ERR_INVALID_ARG;
+    BinetConsts c;
+    rc = lp_make_binet_consts(M, R_S, r_obs, phi_max, h_max, &c);
+    if (rc != LP_OK) return rc;
+    TraceArgs a = {};
+    a.n = n; a.out_fa = out_fa32; a.out_w = out_w16; a.out_alpha32 = out_alpha32;
+    a.out_status = out_status; a.out_steps = out_steps; a.stats = stats; a.row0 = row0;
+    return launch_trace<SRC_CAM, false>(a, c, cam, flags, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------
+// Fully fused frame: pixel -> alpha(f32) -> trace -> fa(f32), w(u16) -> remap -> pixel.
+// Same per-ray code as the kernels above followed by remap_pixel() on the float32-rounded
+// result, so the output is bit-identical to trace_frame + remap run back to back.
+// ---------------------------------------------------------------------------
+template <bool FUSED, typename T>
+__global__ void __launch_bounds__(LP_TRACE_BLOCK)
+lp_render_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts c, const CamConsts cam)
+{
+    StatAcc acc;
+    acc.init();
+    unsigned long long n_mine = 0;
+    const long long stride = (long long)gridDim.x * LP_TRACE_BLOCK;
+    for (long long base = (long long)blockIdx.x * LP_TRACE_BLOCK; base < a.n; base += stride) {
+        const long long i = base + threadIdx.x;
+        const bool live = i < a.n;
+        RayResult r;
+        r.status = 0; r.steps = 0; r.nh = 0; r.fa = 0.0;
+        if (live) {
+            const int row = a.row0 + (int)(i / cam.width);
+            const int col = (int)(i % cam.width);
+            const float a32 = (float)pixel_alpha64(cam, cam_coord(col, cam.half_w, cam.fx),
+                                                   cam_coord(row, cam.half_h, cam.fy));
+            binet_trace<FUSED>(c, (double)a32, r);
+            const float fa32 = (float)((r.status == 1) ? r.fa : __longlong_as_double(0x7ff8000000000000LL));
+            const long long nh = r.nh < 0 ? 0 : (r.nh > 65535 ? 65535 : r.nh);
+            if (a.out_fa) ((float *)a.out_fa)[i] = fa32;
+            if (a.out_w) ((unsigned short *)a.out_w)[i] = (unsigned short)nh;
+            remap_pixel<T>(ra, cam, i, fa32, (unsigned)nh);
+            n_mine++;
+        }
+        if (a.stats) acc.add(r, live);
+    }
+    if (a.stats) lp_stats_flush(acc, n_mine, a.stats);
+}
+
+template <typename T>
+static int launch_render(const TraceArgs &a, const RemapArgs &ra, const BinetConsts &c,
+                         const CamConsts &cam, uint32_t flags, cudaStream_t stream)
+{
+    const bool fused = (flags & LP_TRACE_FUSED) != 0;
+    const void *fn = fused ? (const void *)lp_render_kernel<true, T> : (const void *)lp_render_kernel<false, T>;
+    int grid = 0;
+    int rc = lp_grid_for(fn, LP_TRACE_BLOCK, &grid);
+    if (rc != LP_OK) return rc;
+    const long long chunks = (a.n + LP_TRACE_BLOCK - 1) / LP_TRACE_BLOCK;
+    if (chunks < grid) grid = (int)chunks;
+    if (fused) lp_render_kernel<true, T><<<grid, LP_TRACE_BLOCK, 0, stream>>>(a, ra, c, cam);
+    else       lp_render_kernel<false, T><<<grid, LP_TRACE_BLOCK, 0, stream>>>(a, ra, c, cam);
+    return lp_check_launch();
+}
+
+extern "C" int lp_render_frame(const void *src, int32_t src_dtype, int32_t channels,
+                               const lp_camera *h_cam, int32_t row0, int32_t rows,
+                               double M, double R_S, double r_obs, double phi_max, double h_max,
+                               int32_t render_loop_around, int32_t sampling,
+                               void *out, float *out_fa32, uint16_t *out_w16,
+                               lp_frame_stats *stats, uint32_t flags, void *stream)
+{
+    CamConsts cam;
+    int rc = lp_make_cam_consts(h_cam, &cam);
+    if (rc != LP_OK) return rc;
+    if (row0 < 0 || rows < 0 || (long long)row0 + rows > cam.height) return LP_ERR_INVALID_ARG;
+    if (channels < 1 || channels > 4) return LP_ERR_INVALID_ARG;
+    if (sampling != LP_SAMPLE_NEAREST && sampling != LP_SAMPLE_BILINEAR) return LP_ERR_INVALID_ARG;
+    const long long n = (long long)rows * cam.width;
+    if (n == 0) return LP_OK;
+    if (!src || !out) return LP_ERR_INVALID_ARG;
+    BinetConsts c;
+    rc = lp_make_binet_consts(M, R_S, r_obs, phi_max, h_max, &c);
+    if (rc != LP_OK) return rc;
+    TraceArgs a = {};
+    a.n = n; a.out_fa = out_fa32; a.out_w = out_w16; a.stats = stats; a.row0 = row0;
+    RemapArgs ra;
+    ra.src = src; ra.out = out; ra.fa32 = nullptr; ra.w16 = nullptr; ra.n = n;
+    ra.row0 = row0; ra.channels = channels; ra.loop_around = render_loop_around; ra.sampling = sampling;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (src_dtype) {
+    case LP_DTYPE_U8: return launch_render<unsigned char>(a, ra, c, cam, flags, st);
+    case LP_DTYPE_F32: return launch_render<float>(a, ra, c, cam, flags, st);
+    case LP_DTYPE_F64: return launch_render<double>(a, ra, c, cam, flags, st);
+    default: return LP_ERR_INVALID_ARG;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// build_alpha_lookup alone (image_lens.py:133-152)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+lp_alpha_lookup_kernel(const CamConsts cam, int row0, long long n, int decimals, double scale,
+                       float *__restrict__ out)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int row = row0 + (int)(i / cam.width);
+        const int col = (int)(i % cam.width);
+        double al = pixel_alpha64(cam, cam_coord(col, cam.half_w, cam.fx),
+                                  cam_coord(row, cam.half_h, cam.fy));
+        if (decimals >= 0) al = __ddiv_rn(rint(mul_(al, scale)), scale);   // np.round(alpha, decimals)
+        out[i] = (float)al;
+    }
+}
+
+extern "C" int lp_build_alpha_lookup(const lp_camera *h_cam, int32_t row0, int32_t rows,
+                                     int32_t decimals, float *out_alpha32, void *stream)
+{
+    CamConsts cam;
+    int rc = lp_make_cam_consts(h_cam, &cam);
+    if (rc != LP_OK) return rc;
+    if (row0 < 0 || rows < 0 || (long long)row0 + rows > cam.height) return LP_ERR_INVALID_ARG;
+    if (decimals > 300) return LP_ERR_INVALID_ARG;
+    const long long n = (long long)rows * cam.width;
+    if (n == 0) return LP_OK;
+    if (!out_alpha32) return LP_ERR_INVALID_ARG;
+    int grid = 0;
+    rc = lp_grid_for((const void *)lp_alpha_lookup_kernel, 256, &grid);
+    if (rc != LP_OK) return rc;
+    const long long chunks = (n + 255) / 256;
+    if (chunks < grid) grid = (int)chunks;
+    double scale = 1.0;
+    for (int i = 0; i < decimals; ++i) scale *= 10.0;
+    lp_alpha_lookup_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cam, row0, n, decimals, scale, out_alpha32);
+    return lp_check_launch();
+}
+
+// ---------------------------------------------------------------------------
+// FP64 pipe micro-benchmark (roofline denominator; see lightpath.h)
+// ---------------------------------------------------------------------------
+__global__ void lp_dfma_kernel(int iters, double *sink)
+{
+    double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3;
+    double a4 = a0 + 4e-3, a5 = a0 + 5e-3, a6 = a0 + 6e-3, a7 = a0 + 7e-3;
+    const double m = 0.999999, b = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
+        a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+    }
+    sink[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+extern "C" int lp_bench_dfma(int32_t blocks, int32_t threads, int32_t iters, double *sink, void *stream)
+{
+    if (blocks <= 0 || threads <= 0 || threads > 1024 || iters < 0 || !sink) return LP_ERR_INVALID_ARG;
+    lp_dfma_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink);
+    return lp_check_launch();
+}

@@ -1,0 +1,240 @@
+"""GPU parity of the frame pipeline: build_alpha_lookup (lp_build_alpha_lookup),
+precompute_final_alpha_lookup (lp_schw_trace_alpha32 / lp_schw_trace_frame), render_lensed_image
+(lp_remap), the fully fused lp_render_frame, the shadow classifier and the frame reductions.
+
+Stage-isolated: each GPU stage is fed the REFERENCE's own upstream array
+from tests/golden/frames_small.npz and compared with the reference's output of that stage;
+end-to-end frames are compared at the north-star pixel tolerance (1/255 in 8-bit).
+"""
+import numpy as np
+import pytest
+
+from conftest import bits_equal
+
+pytestmark = pytest.mark.gpu
+
+TAGS = ("wide", "zoom", "offset", "odd", "bigpsi")
+
+
+def _il():
+    from light_path_tracer_b200 import image_lens
+    return image_lens
+
+
+def _metric(M):
+    from light_path_tracer_b200.metrics import Schwarzschild
+    return Schwarzschild(M)
+
+
+def _f32_ulp_diff(a, b):
+    """Number of float32 steps between a and b (NaN == NaN -> 0)."""
+    ai = np.asarray(a, np.float32).view(np.int32).astype(np.int64)
+    bi = np.asarray(b, np.float32).view(np.int32).astype(np.int64)
+    d = np.abs(ai - bi)
+    d[np.isnan(a) & np.isnan(b)] = 0
+    return d
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_alpha_lookup_golden(native, golden, tag):
+    il = _il()
+    g, m = golden("frames_small.npz"), golden("golden_meta.json")["frames"][tag]
+    a = il.build_alpha_lookup((m["H"], m["W"]), (m["hfov"], m["vfov"]), psi=tuple(m["psi"]))
+    ref = g[tag + "_alpha32"]
+    assert a.dtype == np.float32 and a.shape == ref.shape
+    # fp64 arccos then one rounding to float32: a device/host ulp difference in arccos can
+    # only show where the fp64 value sits on a float32 rounding boundary
+    d = _f32_ulp_diff(a, ref)
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_trace_alpha_table_golden(native, golden, tag):
+    """Reference alpha table in -> final_alpha float32 / winding uint16 out (image_lens.py:155-178)."""
+    il = _il()
+    g, m = golden("frames_small.npz"), golden("golden_meta.json")["frames"][tag]
+    fa, w, n, n_tr = il.precompute_final_alpha_lookup(g[tag + "_alpha32"], m["alpha_crit"], m["r_obs"],
+                                                      _metric(m["M"]))
+    assert fa.dtype == np.float32 and w.dtype == np.uint16 and n == n_tr == m["n_total"]
+    ref_fa, ref_w = g[tag + "_fa32"], g[tag + "_w16"]
+    assert np.array_equal(np.isnan(fa), np.isnan(ref_fa)), "escape/capture pattern differs"
+    assert np.array_equal(w, ref_w)
+    # fp64 agreement to 1e-9 relative means the float32 roundings differ by at most one step
+    assert _f32_ulp_diff(fa, ref_fa).max() <= 1
+    assert (_f32_ulp_diff(fa, ref_fa) > 0).mean() < 1e-3
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_remap_golden(native, golden, tag):
+    """Reference lookups in -> rendered frame out, every source layout the reference supports;
+    integer source index => exact pixel equality."""
+    il = _il()
+    g, m = golden("frames_small.npz"), golden("golden_meta.json")["frames"][tag]
+    fov, psi = (m["hfov"], m["vfov"]), tuple(m["psi"])
+    src = g[tag + "_src"]
+    variants = {"rgb32": src, "rgb8": np.floor(255 * src).astype(np.uint8),
+                "gray32": src[..., 2].copy(), "rgb64": src.astype(np.float64)}
+    for name, s in variants.items():
+        out = il.render_lensed_image(s, g[tag + "_alpha32"], g[tag + "_fa32"], g[tag + "_w16"],
+                                     m["alpha_crit"], fov, False, psi=psi)
+        ref = g[tag + "_render_" + name]
+        assert out.dtype == ref.dtype and out.shape == ref.shape
+        assert np.array_equal(out, ref), "%s/%s: %d pixels differ" % (
+            tag, name, int((out != ref).reshape(ref.shape[0], ref.shape[1], -1).any(-1).sum()))
+    out = il.render_lensed_image(src, g[tag + "_alpha32"], g[tag + "_fa32"], g[tag + "_w16"],
+                                 m["alpha_crit"], fov, True, psi=psi)
+    assert np.array_equal(out, g[tag + "_render_rgb32_loop"])
+    out = il.render_lensed_image(src, g[tag + "_alpha32"], g[tag + "_fa32"], None,
+                                 m["alpha_crit"], fov, False, psi=psi)
+    assert np.array_equal(out, g[tag + "_render_rgb32_nowind"])
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_fused_render_equals_staged(native, golden, tag):
+    """lp_render_frame (one launch) == build_alpha_lookup -> trace -> remap run separately,
+    bit for bit, and within 1/255 of the reference's frame end to end."""
+    import torch
+    il = _il()
+    g, m = golden("frames_small.npz"), golden("golden_meta.json")["frames"][tag]
+    dim, fov, psi = (m["H"], m["W"]), (m["hfov"], m["vfov"]), tuple(m["psi"])
+    metric = _metric(m["M"])
+    src = torch.from_numpy(g[tag + "_src"]).cuda()
+    a = il.build_alpha_lookup(dim, fov, psi=psi, device=True)
+    fa, w, _, _ = il.precompute_final_alpha_lookup(a, m["alpha_crit"], m["r_obs"], metric)
+    staged = il.render_lensed_image(src, a, fa, w, m["alpha_crit"], fov, False, psi=psi)
+    fused, fa2, w2 = il.render_frame(src, fov, m["r_obs"], metric, psi=psi, return_lookups=True)
+    assert torch.equal(staged, fused)
+    assert torch.equal(fa.view(torch.int32), fa2.view(torch.int32))
+    assert torch.equal(w.view(torch.int16), w2.view(torch.int16))
+    ref8 = np.floor(g[tag + "_render_rgb32"] * 255)
+    out8 = np.floor(fused.cpu().numpy() * 255)
+    bad = (np.abs(ref8 - out8) > 1).any(-1)
+    # an alpha that differs by one float32 step can move a pixel across a checker edge;
+    # none is expected at this size
+    assert bad.sum() == 0, "%d pixels off by more than 1/255" % int(bad.sum())
+
+
+def test_row_tiles_equal_full_frame(native):
+    """Row-tile sharding (what each GPU gets) reproduces the full frame bit for bit."""
+    import torch
+    il = _il()
+    H, W = 270, 480
+    vfov = np.radians(40.0)
+    fov = (2 * np.arctan(np.tan(vfov / 2) * W / H), vfov)
+    metric = _metric(1.0)
+    src = torch.rand(H, W, 3, device="cuda")
+    full = il.render_frame(src, fov, 100.0, metric, psi=(0.02, -0.03))
+    for parts in (2, 4, 7, 8):
+        bounds = [H * k // parts for k in range(parts + 1)]
+        tiles = [il.render_frame(src, fov, 100.0, metric, psi=(0.02, -0.03), rows=(bounds[k], bounds[k + 1] - bounds[k]))
+                 for k in range(parts)]
+        assert torch.equal(torch.cat(tiles, 0), full)
+
+
+def test_frame_256_stats(native, golden):
+    """Frame reductions (kernel 3) against the reference's 256x256 default frame
+    (escaped 64495 / captured 1040 / invalid 1 / winding 384,
+    sum of steps 3896693, max 200)."""
+    import torch
+    from light_path_tracer_b200 import _device as dev
+    g = golden("frame_256.npz")
+    metric = _metric(1.0)
+    stats = dev.new_stats()
+    a = torch.from_numpy(g["alpha32"]).cuda()
+    st = torch.empty(a.shape, dtype=torch.int8, device="cuda")
+    steps = torch.empty(a.shape, dtype=torch.int32, device="cuda")
+    fa, w = metric.trace_alpha_table(a, 100.0, status=st, steps=steps, stats=stats)
+    s = dev.read_stats(stats)
+    assert np.array_equal(st.cpu().numpy(), g["status"])
+    assert (s["n_rays"], s["n_escaped"], s["n_captured"], s["n_invalid"], s["n_winding"]) == \
+        (65536, 64495, 1040, 1, 384)
+    assert s["sum_steps"] == 3896693 and s["max_steps"] == 200 and s["max_winding"] == 3
+    assert s["sum_steps"] == int(steps.sum().item())
+    assert 0.5 < s["lane_efficiency"] <= 1.0
+    fa_np = fa.cpu().numpy()
+    assert abs(s["min_final_alpha"] - np.nanmin(fa_np)) <= 1e-6 * np.nanmin(fa_np) + 1e-12
+    assert abs(s["max_final_alpha"] - np.nanmax(fa_np)) <= 1e-6
+    # stand-alone reduction over the finished lookups gives the same counts
+    stats2 = dev.new_stats()
+    from light_path_tracer_b200 import _lib
+    _lib.ext().stats_reduce(fa, w, st, steps, stats2)
+    s2 = dev.read_stats(stats2)
+    for k in ("n_rays", "n_escaped", "n_captured", "n_invalid", "n_winding", "sum_steps", "max_steps",
+              "max_winding"):
+        assert s[k] == s2[k], k
+
+
+def test_frame_symmetry_4k(native):
+    """Full-size property (no oracle needed): at psi = 0 rows y and H-y (and columns x, W-x)
+    see the same alpha, so the lookups must be mirror images bit for bit; and the frame
+    counts must match the analytic shadow: captured pixels == pixels with alpha < alpha_sep."""
+    import torch
+    from light_path_tracer_b200 import _device as dev
+    il = _il()
+    H, W = 2160, 3840
+    vfov = np.radians(40.0)
+    fov = (2 * np.arctan(np.tan(vfov / 2) * W / H), vfov)
+    metric = _metric(1.0)
+    stats = dev.new_stats()
+    a = il.build_alpha_lookup((H, W), fov, device=True)
+    fa, w = metric.trace_alpha_table(a, 100.0, stats=stats)
+    fa_i = fa.view(torch.int32)
+    assert torch.equal(fa_i[1:], fa_i[1:].flip(0))
+    assert torch.equal(fa_i[:, 1:], fa_i[:, 1:].flip(1))
+    assert torch.equal(w.view(torch.int16)[1:], w.view(torch.int16)[1:].flip(0))
+    s = dev.read_stats(stats)
+    # SURVEY.md Appendix A, 2160x3840 default frame (alpha from the survey host's numpy;
+    # +-few pixels allowed for arccos ulp differences at float32 rounding boundaries)
+    assert s["n_rays"] == H * W and s["n_invalid"] == 1
+    assert abs(s["n_escaped"] - 8221031) <= 8 and abs(s["n_captured"] - 73368) <= 8
+    assert abs(s["n_winding"] - 26872) <= 8
+    assert abs(s["sum_steps"] - 459558513) <= 5000 and s["max_steps"] >= 200
+
+
+def test_shadow_golden(native, golden):
+    from light_path_tracer_b200 import black_hole_shadow as bs
+    g = golden("shadow.npz")
+    metric = _metric(1.0)
+    img, n_dark = bs.shadow_image(metric, 64, 48, float(g["fov_64x48"]), float(g["r_obs"]), return_count=True)
+    assert img.dtype == np.float64 and img.shape == (64, 48)
+    assert np.array_equal(img, g["image_64x48"]) and n_dark == int((g["image_64x48"] == 0).sum())
+    img = bs.shadow_image(metric, 80, 80, float(g["fov_80x80"]), float(g["r_obs"]))
+    assert np.array_equal(img, g["image_80x80"])
+
+
+def test_shadow_256_vs_oracle(native, oracle):
+    """BASELINE.json config 1: the black_hole_shadow computation at 256x256 (fov 40 deg, r_obs 50 M)."""
+    from light_path_tracer_b200 import black_hole_shadow as bs
+    metric = _metric(1.0)
+    fov = np.radians(40)
+    img = bs.shadow_image(metric, 256, 256, fov, 50.0)
+    ref = oracle.shadow_image(256, 256, fov, float(metric.alpha_crit(50.0)))
+    assert np.array_equal(img, ref)
+    assert set(np.unique(img)) <= {0.0, 1.0}
+
+
+def test_frame_1080p_vs_oracle(native, oracle):
+    """BASELINE.json config 2 (1920x1080 checkerboard) against the oracle, stage by stage."""
+    import torch
+    il = _il()
+    H, W = 1080, 1920
+    vfov = np.radians(40.0)
+    fov = (2 * np.arctan(np.tan(vfov / 2) * W / H), vfov)
+    metric = _metric(1.0)
+    a_ref = oracle.build_alpha_lookup((H, W), fov)
+    a = il.build_alpha_lookup((H, W), fov)
+    d = _f32_ulp_diff(a, a_ref)
+    assert d.max() <= 1 and (d > 0).sum() <= 16
+    fa_ref, w_ref, _, _ = oracle.precompute_final_alpha_lookup(a_ref, 1.0, 100.0)
+    fa, w, _, _ = il.precompute_final_alpha_lookup(a_ref, metric.alpha_crit(100.0), 100.0, metric)
+    assert np.array_equal(np.isnan(fa), np.isnan(fa_ref)) and np.array_equal(w, w_ref)
+    d = _f32_ulp_diff(fa, fa_ref)
+    assert d.max() <= 1 and (d > 0).sum() <= 16
+    src = oracle.checkerboard(H, W)
+    ref = oracle.render_lensed_image(src, fa_ref, w_ref, fov)
+    out = il.render_lensed_image(src, a_ref, fa_ref, w_ref, 0.0, fov)
+    assert np.array_equal(out, ref)
+    # end to end, fused, device resident
+    fused = il.render_frame(torch.from_numpy(src).cuda(), fov, 100.0, metric).cpu().numpy()
+    bad = (np.abs(np.floor(fused * 255) - np.floor(ref * 255)) > 1).any(-1)
+    assert bad.sum() <= 4, "%d pixels differ by more than 1/255" % int(bad.sum())

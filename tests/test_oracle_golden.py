@@ -1,0 +1,91 @@
+"""CPU: pin the oracle (oracle/lp_oracle.*) to the fixtures generated from the
+UNMODIFIED reference (tests/golden/make_golden.py).  Bit-exact everywhere."""
+import numpy as np
+
+from conftest import bits_equal
+
+
+def test_binet_known_answers(oracle, golden):
+    g = golden("binet_known_answers.npz")
+    n = g["alpha"].size
+    assert n > 1000
+    for i in range(n):
+        M, r_obs, a = float(g["M"][i]), float(g["r_obs"][i]), float(g["alpha"][i])
+        so, phi, u, w, _ = oracle.binet_orbit(M, 2 * M, r_obs, a)
+        assert so == g["orbit_status"][i]
+        assert bits_equal([phi, u, w], [g["phi_f"][i], g["u_f"][i], g["w_f"][i]]), (M, r_obs, a)
+        sr, fa, nh, _ = oracle.binet_ray(M, 2 * M, r_obs, a)
+        assert sr == g["ray_status"][i] == g["api_outcome"][i]
+        assert bits_equal([fa], [g["final_alpha"][i]])
+        assert nh == g["n_half"][i]
+
+
+def test_separatrix_adjacent_doubles(oracle, golden):
+    meta = golden("golden_meta.json")["separatrix_hex"]
+    for key, (lo, hi) in meta.items():
+        M = float(key.split("_")[0][1:])
+        r_obs = float(key.split("_r")[1])
+        lo, hi = float.fromhex(lo), float.fromhex(hi)
+        assert np.nextafter(lo, 1.0) == hi
+        assert oracle.binet_ray(M, 2 * M, r_obs, lo)[0] == -1
+        assert oracle.binet_ray(M, 2 * M, r_obs, hi)[0] == 1
+
+
+def test_batch(oracle, golden):
+    g = golden("binet_batch.npz")
+    for tag in ("r100", "r15", "m2p5_r40"):
+        fa, w, st, steps = oracle.trace_rays_batch(float(g[tag + "_M"]), float(g[tag + "_r_obs"]),
+                                                    g[tag + "_alpha"])
+        assert bits_equal(fa, g[tag + "_fa"])
+        assert np.array_equal(w, g[tag + "_w"])
+        assert ((st == 1) == np.isfinite(g[tag + "_fa"])).all()
+
+
+def test_frames(oracle, golden):
+    g = golden("frames_small.npz")
+    meta = golden("golden_meta.json")["frames"]
+    for tag in ("wide", "zoom", "offset", "odd", "bigpsi"):
+        m = meta[tag]
+        dim, fov, psi = (m["H"], m["W"]), (m["hfov"], m["vfov"]), tuple(m["psi"])
+        assert np.array_equal(oracle.build_alpha_lookup(dim, fov, psi=psi), g[tag + "_alpha32"])
+        fa, w, n, n2 = oracle.precompute_final_alpha_lookup(g[tag + "_alpha32"], m["M"], m["r_obs"])
+        assert bits_equal(fa, g[tag + "_fa32"]) and np.array_equal(w, g[tag + "_w16"])
+        assert n == n2 == m["n_total"]
+        src = g[tag + "_src"]
+        variants = {"rgb32": src, "rgb8": np.floor(255 * src).astype(np.uint8),
+                    "gray32": src[..., 2].copy(), "rgb64": src.astype(np.float64)}
+        for name, s in variants.items():
+            r = oracle.render_lensed_image(s, g[tag + "_fa32"], g[tag + "_w16"], fov, False, psi)
+            ref = g[tag + "_render_" + name]
+            assert r.dtype == ref.dtype and np.array_equal(r, ref), (tag, name)
+        assert np.array_equal(oracle.render_lensed_image(src, g[tag + "_fa32"], g[tag + "_w16"], fov, True, psi),
+                              g[tag + "_render_rgb32_loop"])
+        assert np.array_equal(oracle.render_lensed_image(src, g[tag + "_fa32"], None, fov, False, psi),
+                              g[tag + "_render_rgb32_nowind"])
+
+
+def test_frame_256_aggregates(oracle, golden):
+    g = golden("frame_256.npz")
+    agg = golden("golden_meta.json")["frame_256"]
+    fa, w, n, _, st, steps = oracle.precompute_final_alpha_lookup(g["alpha32"], agg["M"], agg["r_obs"],
+                                                                   want_status=True)
+    assert bits_equal(fa, g["fa32"]) and np.array_equal(w, g["w16"]) and np.array_equal(st, g["status"])
+    s = oracle.frame_stats(fa, w, st, steps)
+    for k in ("escaped", "captured", "invalid", "winding", "max_winding"):
+        assert s[k] == agg[k], k
+    # SURVEY.md Appendix A (survey session, same reference): 256x256 default frame
+    assert (s["escaped"], s["captured"], s["invalid"], s["winding"]) == (64495, 1040, 1, 384)
+    assert s["sum_steps"] == 3896693 and s["max_steps"] == 200
+
+
+def test_shadow(oracle, golden):
+    g = golden("shadow.npz")
+    ac = float(g["alpha_crit"])
+    assert np.array_equal(oracle.shadow_image(64, 48, float(g["fov_64x48"]), ac), g["image_64x48"])
+    assert np.array_equal(oracle.shadow_image(80, 80, float(g["fov_80x80"]), ac), g["image_80x80"])
+
+
+def test_alpha_crit(oracle):
+    # SURVEY.md Appendix A
+    assert oracle.alpha_crit(1.0, 50.0) == 0.10200015330371326
+    assert oracle.alpha_crit(1.0, 100.0) == 0.051461996376274736
