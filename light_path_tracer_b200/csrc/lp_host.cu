@@ -114,6 +114,19 @@ int lp_make_binet_consts(double M, double R_S, double r_obs, double phi_max, dou
     return LP_OK;
 }
 
+// Fast-path precondition: positive finite band, observer strictly inside it, and at least
+// one representable high word strictly between the bounds' high words.
+int lp_binet_fast_ok(const BinetConsts *c)
+{
+    if (!(c->uc > 0.0) || !(c->ue > 0.0) || !isfinite(c->uc) || !isfinite(c->ue)) return 0;
+    if (!(c->ue < c->u0 && c->u0 < c->uc)) return 0;
+    unsigned long long bc, be;
+    memcpy(&bc, &c->uc, 8);
+    memcpy(&be, &c->ue, 8);
+    const unsigned hc = (unsigned)(bc >> 32), he = (unsigned)(be >> 32);
+    return hc > he + 1u;
+}
+
 int lp_make_cam_consts(const lp_camera *cam, CamConsts *o)
 {
     if (!cam || cam->height < 0 || cam->width < 0) return LP_ERR_INVALID_ARG;

@@ -1,15 +1,18 @@
 // lp_trace.cu — kernel (1a): one-thread-per-ray Schwarzschild Binet-equation RK4 tracer
 // (replaces metrics.py:49-145, :661-668 and the drivers at image_lens.py:133-178).
 //
-// Layout: persistent grid (resident CTAs x SM count), each CTA walks 256-ray chunks
-// round-robin, a warp owns 32 consecutive rays (= 32 consecutive pixels of a row), so
+// Layout: one thread per ray, small CTAs (64 rays) back-filled by the hardware work
+// distributor; a warp owns 32 consecutive rays (= 32 consecutive pixels of a row), so
 // the alpha loads and the fa / winding stores are fully coalesced.  The ray state
 // (u, w, step index) lives in registers in fp64; the per-configuration constants and the
 // strided phi table arrive through the kernel parameter (constant) bank.
 #include "lp_internal.cuh"
 #include "lp_remap.cuh"
 
-#define LP_TRACE_BLOCK 256
+#include <stdlib.h>
+
+#define LP_TRACE_BLOCK 256          /* launch bound (max threads per CTA) */
+#define LP_TRACE_DEFAULT_BLOCK 64   /* rays per CTA; LP_TRACE_BLOCK=32|64|128|256 overrides (tuning) */
 
 enum { SRC_F64 = 0, SRC_F32 = 1, SRC_CAM = 2 };
 
@@ -25,51 +28,66 @@ struct TraceArgs {
     int32_t row0;           // SRC_CAM: first frame row of the tile
 };
 
-template <bool FUSED, int SRC, bool WIDE>
+// One ray per thread, one CTA per `blockDim.x` consecutive rays.  The grid is NOT
+// persistent on purpose: the SMSP arbiter is unfair between always-eligible warps, so a
+// resident-forever grid finishes its warps at very different times and the tail runs
+// under-occupied (ncu, round 1: 5.6 of 8 warps active on average); small CTAs let the
+// hardware work distributor back-fill SMs as warps retire.
+template <bool FUSED, bool FAST, int SRC, bool WIDE>
 __global__ void __launch_bounds__(LP_TRACE_BLOCK)
 lp_trace_kernel(const TraceArgs a, const BinetConsts c, const CamConsts cam)
 {
-    StatAcc acc;
-    acc.init();
-    unsigned long long n_mine = 0;
-    const long long stride = (long long)gridDim.x * LP_TRACE_BLOCK;
-    for (long long base = (long long)blockIdx.x * LP_TRACE_BLOCK; base < a.n; base += stride) {
-        const long long i = base + threadIdx.x;
-        const bool live = i < a.n;
-        RayResult r;
-        r.status = 0; r.steps = 0; r.nh = 0; r.fa = 0.0;
-        if (live) {
-            double alpha;
-            if (SRC == SRC_F64) {
-                alpha = __ldg((const double *)a.alphas + i);
-            } else if (SRC == SRC_F32) {
-                alpha = (double)__ldg((const float *)a.alphas + i);   // image_lens.py:157
-            } else {
-                const int row = a.row0 + (int)(i / cam.width);
-                const int col = (int)(i % cam.width);
-                const double xc = cam_coord(col, cam.half_w, cam.fx);
-                const double yc = cam_coord(row, cam.half_h, cam.fy);
-                const float a32 = (float)pixel_alpha64(cam, xc, yc);     // image_lens.py:152
-                if (a.out_alpha32) a.out_alpha32[i] = a32;
-                alpha = (double)a32;
-            }
-            binet_trace<FUSED>(c, alpha, r);
-            const double fa = (r.status == 1) ? r.fa : __longlong_as_double(0x7ff8000000000000LL);
-            if (WIDE) {
-                ((double *)a.out_fa)[i] = fa;                          // metrics.py:667
-                ((long long *)a.out_w)[i] = r.nh;                      // metrics.py:668
-            } else {
-                ((float *)a.out_fa)[i] = (float)fa;                    // image_lens.py:176
-                const long long nh = r.nh < 0 ? 0 : (r.nh > 65535 ? 65535 : r.nh);
-                ((unsigned short *)a.out_w)[i] = (unsigned short)nh;   // image_lens.py:177
-            }
-            if (a.out_status) a.out_status[i] = (int8_t)r.status;
-            if (a.out_steps) a.out_steps[i] = r.steps;
-            n_mine++;
+    const LoopRegs L = load_loop_regs(c);
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < a.n;
+    RayResult r;
+    r.status = 0; r.steps = 0; r.nh = 0; r.fa = 0.0;
+    if (live) {
+        double alpha;
+        if (SRC == SRC_F64) {
+            alpha = __ldg((const double *)a.alphas + i);
+        } else if (SRC == SRC_F32) {
+            alpha = (double)__ldg((const float *)a.alphas + i);   // image_lens.py:157
+        } else {
+            const int row = a.row0 + (int)(i / cam.width);
+            const int col = (int)(i % cam.width);
+            const double xc = cam_coord(col, cam.half_w, cam.fx);
+            const double yc = cam_coord(row, cam.half_h, cam.fy);
+            const float a32 = (float)pixel_alpha64(cam, xc, yc);     // image_lens.py:152
+            if (a.out_alpha32) a.out_alpha32[i] = a32;
+            alpha = (double)a32;
         }
-        if (a.stats) acc.add(r, live);
+        binet_trace<FUSED, FAST>(c, L, alpha, r);
+        const double fa = (r.status == 1) ? r.fa : __longlong_as_double(0x7ff8000000000000LL);
+        if (WIDE) {
+            ((double *)a.out_fa)[i] = fa;                          // metrics.py:667
+            ((long long *)a.out_w)[i] = r.nh;                      // metrics.py:668
+        } else {
+            ((float *)a.out_fa)[i] = (float)fa;                    // image_lens.py:176
+            const long long nh = r.nh < 0 ? 0 : (r.nh > 65535 ? 65535 : r.nh);
+            ((unsigned short *)a.out_w)[i] = (unsigned short)nh;   // image_lens.py:177
+        }
+        if (a.out_status) a.out_status[i] = (int8_t)r.status;
+        if (a.out_steps) a.out_steps[i] = r.steps;
     }
-    if (a.stats) lp_stats_flush(acc, n_mine, a.stats);
+    if (a.stats) {
+        StatAcc acc;
+        acc.init();
+        acc.add(r, live);
+        lp_stats_flush(acc, live ? 1ull : 0ull, a.stats);
+    }
+}
+
+static int trace_block_size()
+{
+    static int cached = 0;
+    if (!cached) {
+        int v = LP_TRACE_DEFAULT_BLOCK;
+        const char *e = getenv("LP_TRACE_BLOCK");
+        if (e) { const int t = atoi(e); if (t == 32 || t == 64 || t == 128 || t == 256) v = t; }
+        cached = v;
+    }
+    return cached;
 }
 
 template <int SRC, bool WIDE>
@@ -78,15 +96,18 @@ static int launch_trace(const TraceArgs &a, const BinetConsts &c, const CamConst
 {
     if (a.n == 0) return LP_OK;
     const bool fused = (flags & LP_TRACE_FUSED) != 0;
-    const void *fn = fused ? (const void *)lp_trace_kernel<true, SRC, WIDE>
-                           : (const void *)lp_trace_kernel<false, SRC, WIDE>;
-    int grid = 0;
-    int rc = lp_grid_for(fn, LP_TRACE_BLOCK, &grid);
-    if (rc != LP_OK) return rc;
-    const long long chunks = (a.n + LP_TRACE_BLOCK - 1) / LP_TRACE_BLOCK;
-    if (chunks < grid) grid = (int)chunks;
-    if (fused) lp_trace_kernel<true, SRC, WIDE><<<grid, LP_TRACE_BLOCK, 0, stream>>>(a, c, cam);
-    else       lp_trace_kernel<false, SRC, WIDE><<<grid, LP_TRACE_BLOCK, 0, stream>>>(a, c, cam);
+    const bool icmp = lp_binet_fast_ok(&c) != 0;
+    const int block = trace_block_size();
+    const long long chunks = (a.n + block - 1) / block;
+    if (chunks > 0x7fffffffLL) return LP_ERR_UNSUPPORTED;
+    const unsigned grid = (unsigned)chunks;
+    if (fused) {
+        if (icmp) lp_trace_kernel<true, true, SRC, WIDE><<<grid, block, 0, stream>>>(a, c, cam);
+        else      lp_trace_kernel<true, false, SRC, WIDE><<<grid, block, 0, stream>>>(a, c, cam);
+    } else {
+        if (icmp) lp_trace_kernel<false, true, SRC, WIDE><<<grid, block, 0, stream>>>(a, c, cam);
+        else      lp_trace_kernel<false, false, SRC, WIDE><<<grid, block, 0, stream>>>(a, c, cam);
+    }
     return lp_check_launch();
 }
 
@@ -155,35 +176,33 @@ extern "C" int lp_schw_trace_frame(const lp_camera *h_cam, int32_t row0, int32_t
 // Same per-ray code as the kernels above followed by remap_pixel() on the float32-rounded
 // result, so the output is bit-identical to trace_frame + remap run back to back.
 // ---------------------------------------------------------------------------
-template <bool FUSED, typename T>
+template <bool FUSED, bool FAST, typename T>
 __global__ void __launch_bounds__(LP_TRACE_BLOCK)
 lp_render_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts c, const CamConsts cam)
 {
-    StatAcc acc;
-    acc.init();
-    unsigned long long n_mine = 0;
-    const long long stride = (long long)gridDim.x * LP_TRACE_BLOCK;
-    for (long long base = (long long)blockIdx.x * LP_TRACE_BLOCK; base < a.n; base += stride) {
-        const long long i = base + threadIdx.x;
-        const bool live = i < a.n;
-        RayResult r;
-        r.status = 0; r.steps = 0; r.nh = 0; r.fa = 0.0;
-        if (live) {
-            const int row = a.row0 + (int)(i / cam.width);
-            const int col = (int)(i % cam.width);
-            const float a32 = (float)pixel_alpha64(cam, cam_coord(col, cam.half_w, cam.fx),
-                                                   cam_coord(row, cam.half_h, cam.fy));
-            binet_trace<FUSED>(c, (double)a32, r);
-            const float fa32 = (float)((r.status == 1) ? r.fa : __longlong_as_double(0x7ff8000000000000LL));
-            const long long nh = r.nh < 0 ? 0 : (r.nh > 65535 ? 65535 : r.nh);
-            if (a.out_fa) ((float *)a.out_fa)[i] = fa32;
-            if (a.out_w) ((unsigned short *)a.out_w)[i] = (unsigned short)nh;
-            remap_pixel<T>(ra, cam, i, fa32, (unsigned)nh);
-            n_mine++;
-        }
-        if (a.stats) acc.add(r, live);
+    const LoopRegs L = load_loop_regs(c);
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < a.n;
+    RayResult r;
+    r.status = 0; r.steps = 0; r.nh = 0; r.fa = 0.0;
+    if (live) {
+        const int row = a.row0 + (int)(i / cam.width);
+        const int col = (int)(i % cam.width);
+        const float a32 = (float)pixel_alpha64(cam, cam_coord(col, cam.half_w, cam.fx),
+                                               cam_coord(row, cam.half_h, cam.fy));
+        binet_trace<FUSED, FAST>(c, L, (double)a32, r);
+        const float fa32 = (float)((r.status == 1) ? r.fa : __longlong_as_double(0x7ff8000000000000LL));
+        const long long nh = r.nh < 0 ? 0 : (r.nh > 65535 ? 65535 : r.nh);
+        if (a.out_fa) ((float *)a.out_fa)[i] = fa32;
+        if (a.out_w) ((unsigned short *)a.out_w)[i] = (unsigned short)nh;
+        remap_pixel<T>(ra, cam, i, fa32, (unsigned)nh);
     }
-    if (a.stats) lp_stats_flush(acc, n_mine, a.stats);
+    if (a.stats) {
+        StatAcc acc;
+        acc.init();
+        acc.add(r, live);
+        lp_stats_flush(acc, live ? 1ull : 0ull, a.stats);
+    }
 }
 
 template <typename T>
@@ -191,14 +210,18 @@ static int launch_render(const TraceArgs &a, const RemapArgs &ra, const BinetCon
                          const CamConsts &cam, uint32_t flags, cudaStream_t stream)
 {
     const bool fused = (flags & LP_TRACE_FUSED) != 0;
-    const void *fn = fused ? (const void *)lp_render_kernel<true, T> : (const void *)lp_render_kernel<false, T>;
-    int grid = 0;
-    int rc = lp_grid_for(fn, LP_TRACE_BLOCK, &grid);
-    if (rc != LP_OK) return rc;
-    const long long chunks = (a.n + LP_TRACE_BLOCK - 1) / LP_TRACE_BLOCK;
-    if (chunks < grid) grid = (int)chunks;
-    if (fused) lp_render_kernel<true, T><<<grid, LP_TRACE_BLOCK, 0, stream>>>(a, ra, c, cam);
-    else       lp_render_kernel<false, T><<<grid, LP_TRACE_BLOCK, 0, stream>>>(a, ra, c, cam);
+    const bool icmp = lp_binet_fast_ok(&c) != 0;
+    const int block = trace_block_size();
+    const long long chunks = (a.n + block - 1) / block;
+    if (chunks > 0x7fffffffLL) return LP_ERR_UNSUPPORTED;
+    const unsigned grid = (unsigned)chunks;
+    if (fused) {
+        if (icmp) lp_render_kernel<true, true, T><<<grid, block, 0, stream>>>(a, ra, c, cam);
+        else      lp_render_kernel<true, false, T><<<grid, block, 0, stream>>>(a, ra, c, cam);
+    } else {
+        if (icmp) lp_render_kernel<false, true, T><<<grid, block, 0, stream>>>(a, ra, c, cam);
+        else      lp_render_kernel<false, false, T><<<grid, block, 0, stream>>>(a, ra, c, cam);
+    }
     return lp_check_launch();
 }
 
