@@ -56,6 +56,8 @@ def lib():
         L.lp_oracle_binet_ray.argtypes = [d, d, d, d, d, d] + [vp] * 3
         L.lp_oracle_trace_rays_batch.restype = None
         L.lp_oracle_trace_rays_batch.argtypes = [d, d, d, vp, i64, d, d, vp, vp, vp, vp]
+        L.lp_oracle_trace_rays_batch_shift.restype = None
+        L.lp_oracle_trace_rays_batch_shift.argtypes = [d, d, d, vp, i64, ctypes.c_int, d, d, vp, vp, vp]
         L.lp_oracle_trace_frame_f32.restype = None
         L.lp_oracle_trace_frame_f32.argtypes = [d, d, d, vp, i64, d, d, vp, vp, vp, vp]
         L.lp_oracle_shadow.restype = None
@@ -113,6 +115,20 @@ def trace_rays_batch(M, r_obs, alphas, phi_max=PHI_MAX, h_max=H_MAX, R_S=None,
     lib().lp_oracle_trace_rays_batch(M, R_S, r_obs, _p(alphas), n, phi_max, h_max,
                                      _p(fa), _p(w), _p(st), _p(steps))
     return fa, w, st, steps
+
+
+def trace_rays_batch_sin_shift(M, r_obs, alphas, sin_shift, phi_max=PHI_MAX, h_max=H_MAX):
+    """Sensitivity probe, not a reference path: trace_rays_batch with np.sin(alpha)
+    (metrics.py:55 — the one libm-dependent input of the integration) moved by
+    ``sin_shift`` ulps.  -> (out_fa, out_w, status)."""
+    alphas = np.ascontiguousarray(alphas, dtype=np.float64)
+    n = alphas.size
+    fa = np.empty(n, np.float64)
+    w = np.empty(n, np.int64)
+    st = np.empty(n, np.int8)
+    lib().lp_oracle_trace_rays_batch_shift(M, 2 * M, r_obs, _p(alphas), n, int(sin_shift),
+                                           phi_max, h_max, _p(fa), _p(w), _p(st))
+    return fa, w, st
 
 
 def precompute_final_alpha_lookup(alpha_lookup, M, r_obs, want_status=False):
