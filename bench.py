@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py — geodesic rays/s and ms/frame of the 4K Schwarzschild lensed render.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json metric "geodesic rays/sec and ms/frame at 4K"):
+the image_lens pipeline — per-pixel viewing angle (float32 table semantics) -> Binet RK4
+null-geodesic trace (fp64, the reference's own stepper, strict arithmetic) -> deflection
+remap of a synthetic float32 RGB checkerboard — at 3840x2160, M=1, r_obs=100 M, vertical
+FOV 40 deg, psi=(0,0).  One step = one frame = ONE launch of the fused kernel
+(lp_render_frame).  N > 1: weak scaling by row tiles — the frame grows to 3840 x (2160 N),
+rank g renders its 2160-row tile and the tiles are gathered to rank 0 over NCCL.
+
+Prints ONE JSON line on rank 0 (contract in the task statement): value = whole-job rays/s
+with the source image resident in HBM; e2e = the same through the host-buffer API with the
+H2D copy of the source and the D2H copy of the frame inside the timed region; roofline =
+the fused kernel's algorithmic fp64 flops (43/RK4 step + 40/ray) over its
+CUDA-event time against the FP64 peak MEASURED in this run by a DFMA micro-benchmark
+(MEASURED_PEAKS.json has no fp64 figure); cpu_baseline = the oracle (C/numpy port of the
+reference's CPU path) timed on this box's host cores on one full frame.
+
+--impl reference times that CPU port alone (all host threads), one bounded sample per step.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+H0, W0 = 2160, 3840
+M, R_OBS, VFOV_DEG = 1.0, 100.0, 40.0
+FLOP_PER_STEP, FLOP_PER_RAY = 43, 40     # SURVEY.md §8d work model of the integrator
+
+
+def fov_for(H, W):
+    vfov = np.radians(VFOV_DEG)
+    return (2 * np.arctan(np.tan(vfov / 2) * W / H), vfov)   # image_lens.py:461-463
+
+
+# ---------------------------------------------------------------------------------------
+# clocks / throttle reasons during the timed region (NVML, sampled from a thread)
+# ---------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+                 "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        return {"sm_mhz": int(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------
+# CPU legs (oracle port of the reference's numpy/numba path) — checker code, timed only
+# ---------------------------------------------------------------------------------------
+def cpu_frame(O, H, W, rows=None):
+    """build_alpha_lookup -> precompute_final_alpha_lookup -> render_lensed_image on the host
+    (image_lens.py:480-505) for the frame rows `rows` (None = all).  Returns (seconds, rays)."""
+    fov = fov_for(H, W)
+    src = O.checkerboard(H, W)
+    t0 = time.perf_counter()
+    alpha = O.build_alpha_lookup((H, W), fov, rows=rows)
+    fa, w, n, _ = O.precompute_final_alpha_lookup(alpha, M, R_OBS)
+    O.render_lensed_image(src, fa, w, fov, rows=rows)
+    return time.perf_counter() - t0, int(alpha.size)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import lp_oracle as O
+    O.build()
+    H, W = H0 * args.gpus, W0
+    rows = np.arange(0, H, 8)              # bounded sample: every 8th row of the frame
+    for _ in range(args.warmup):
+        cpu_frame(O, H, W, rows)
+    times, rays = [], 0
+    for _ in range(args.steps):
+        t, rays = cpu_frame(O, H, W, rows)
+        times.append(t)
+    total = float(np.sum(times))
+    value = rays * args.steps / total
+    cores = O.num_threads()
+    sample = "every 8th row of the %dx%d frame (%d rays) per step; trace on %d OpenMP threads, " \
+             "alpha lookup and remap single-threaded numpy like the reference" % (W, H, rays, cores)
+    line = {
+        "impl": "reference", "metric": "geodesic rays/sec (4K Schwarzschild lensed render)",
+        "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus, H, W),
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n, H, W):
+    return {"workload": "image_lens Schwarzschild lensed render %dx%d (alpha lookup -> Binet RK4 trace "
+                        "-> remap), M=1, r_obs=100M, vfov=40deg, psi=(0,0), float32 RGB checkerboard source"
+                        % (W, H),
+            "rays_per_frame": H * W, "rows_per_gpu": H // n,
+            "parallelism": "row tiles x%d, NCCL gather to rank 0" % n if n > 1 else "single GPU",
+            "arithmetic": "strict (separately rounded fp64, bit-identical trajectories)",
+            "l2": "256 MiB buffer written between timed steps (L2 flush)"}
+
+
+# ---------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------
+def measure_fp64_peak(torch, ext):
+    sink = torch.empty(148 * 32 * 256, dtype=torch.float64, device="cuda")
+    iters, best = 20000, None
+    for i in range(6):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ext.bench_dfma(148 * 32, 256, iters, sink)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        if i and (best is None or ms < best):
+            best = ms
+    return 148 * 32 * 256 * iters * 16 / (best * 1e-3) / 1e12
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from light_path_tracer_b200 import _device as dev, _lib
+    from light_path_tracer_b200 import image_lens as il
+    from light_path_tracer_b200 import dist as lpdist
+    from light_path_tracer_b200.metrics import Schwarzschild
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d: launch with torch.distributed.run" % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ext = _lib.ext()
+    N = world
+    H, W = H0 * N, W0
+    fov = fov_for(H, W)
+    metric = Schwarzschild(M)
+    tiles = lpdist.row_tiles(H, N)
+    row0, rows = tiles[rank]
+
+    import lp_oracle as O                          # only for the synthetic source + CPU leg
+    src_host = torch.from_numpy(O.checkerboard(H, W)).pin_memory()
+    src = src_host.to("cuda", non_blocking=True)
+    tile = torch.empty((rows, W, 3), dtype=torch.float32, device="cuda")
+    tile_host = torch.empty((rows, W, 3), dtype=torch.float32).pin_memory()
+    frame = torch.empty((N, rows, W, 3), dtype=torch.float32, device="cuda") if (N > 1 and rank == 0) else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if N > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather():
+        if N > 1:
+            dist.gather(tile, list(frame.unbind(0)) if rank == 0 else None, dst=0)
+
+    def step_resident():
+        il.render_frame(src, fov, R_OBS, metric, rows=(row0, rows), out=tile)
+        gather()
+
+    def step_e2e():
+        d_src = src_host.to("cuda", non_blocking=True)
+        il.render_frame(d_src, fov, R_OBS, metric, rows=(row0, rows), out=tile)
+        tile_host.copy_(tile, non_blocking=True)
+
+    def timed(step, k):
+        """k steps, each bracketed by CUDA events on the launching stream; L2 flushed in between."""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
+        barrier()
+        for a, b in ev:
+            flush.zero_()
+            a.record()
+            step()
+            b.record()
+        barrier()
+        return [a.elapsed_time(b) for a, b in ev]
+
+    # --- untimed: work model numerator (sum of RK4 steps) and kernel-only timings --------
+    stats = dev.new_stats()
+    il.render_frame(src, fov, R_OBS, metric, rows=(row0, rows), out=tile, stats=stats)
+    st = dev.read_stats(stats)
+    flops_tile = FLOP_PER_STEP * st["sum_steps"] + FLOP_PER_RAY * st["n_rays"]
+    peak_tf = measure_fp64_peak(torch, ext)
+
+    for _ in range(args.warmup):
+        step_resident()
+    with ClockSampler(local) as clk:
+        ms = timed(step_resident, args.steps)
+    total_ms = float(np.sum(ms))
+    for _ in range(args.warmup):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    total_e2e = float(np.sum(ms_e2e))
+
+    # dominant kernel alone (no gather), same events: roofline numerator / denominator
+    def step_kernel():
+        il.render_frame(src, fov, R_OBS, metric, rows=(row0, rows), out=tile)
+    ms_k = timed(step_kernel, args.steps)
+    kern_ms = float(np.mean(ms_k))
+
+    extra = {}
+    if rank == 0 and N == 1:
+        a32 = il.build_alpha_lookup((H, W), fov, device=True)
+        fa32, w16 = metric.trace_alpha_table(a32, R_OBS)
+        t_strict = float(np.mean(timed(lambda: metric.trace_alpha_table(a32, R_OBS), args.steps)))
+        t_fused = float(np.mean(timed(lambda: metric.trace_alpha_table(a32, R_OBS, flags=1), args.steps)))
+        t_remap = float(np.mean(timed(lambda: il.render_lensed_image(src, a32, fa32, w16, 0.0, fov), args.steps)))
+        extra = {
+            "trace_kernel_strict": {"ms": t_strict, "rays_per_s": H * W / t_strict * 1e3,
+                                    "tflops": flops_tile / t_strict / 1e9,
+                                    "frac_of_measured_fp64_peak": flops_tile / t_strict / 1e9 / peak_tf},
+            "trace_kernel_fma_contracted": {"ms": t_fused, "rays_per_s": H * W / t_fused * 1e3,
+                                            "tflops": flops_tile / t_fused / 1e9,
+                                            "frac_of_measured_fp64_peak": flops_tile / t_fused / 1e9 / peak_tf},
+            "remap_kernel": {"ms": t_remap, "gb_per_s": H * W * 30 / t_remap / 1e6, "bytes_per_px": 30,
+                             "frac_of_measured_hbm": H * W * 30 / t_remap / 1e6 / hbm_peak()},
+        }
+
+    # max over ranks, on the device
+    if N > 1:
+        t = torch.tensor([total_ms, total_e2e, kern_ms, float(flops_tile), float(st["sum_steps"]),
+                          float(st["sum_warp_steps"])], dtype=torch.float64, device="cuda")
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        total_ms, total_e2e, kern_ms = float(tmax[0]), float(tmax[1]), float(tmax[2])
+        flops_max_tile = float(tmax[3])
+        sum_steps, sum_warp = float(tsum[4]), float(tsum[5])
+    else:
+        flops_max_tile, sum_steps, sum_warp = float(flops_tile), float(st["sum_steps"]), float(st["sum_warp_steps"])
+
+    if rank == 0:
+        rays = H * W
+        value = rays * args.steps / (total_ms * 1e-3)
+        e2e_value = rays * args.steps / (total_e2e * 1e-3)
+        achieved = flops_max_tile / (kern_ms * 1e-3) / 1e12
+        traffic = ncu_traffic()
+        line = {
+            "metric": "geodesic rays/sec (4K Schwarzschild lensed render)",
+            "value": value, "unit": "rays/s", "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(N, H, W),
+            "ms_per_frame": total_ms / args.steps,
+            "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_frame": total_e2e / args.steps,
+                    "h2d_bytes_per_step": int(src_host.numel() * 4 * N),
+                    "d2h_bytes_per_step": int(rays * 12),
+                    "path": "pinned float32 source -> H2D -> lp_render_frame -> D2H pinned float32 frame"},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "fp64", "kernel": "lp_render_kernel (alpha + Binet RK4 + remap, fused)",
+                         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                         "peak_source": "measured in this run: DFMA micro-benchmark lp_bench_dfma "
+                                        "(MEASURED_PEAKS.json has no fp64 entry; nominal 148 SM x 64 FMA/clk x 2 "
+                                        "x 1.965 GHz = 37.2)",
+                         "flop_model": "43 flop per RK4 step + 40 per ray (SURVEY.md 8d); un-fused strict "
+                                       "arithmetic issues 1 flop per FP64-pipe slot, so 0.5 is the pipe's ceiling "
+                                       "for this kernel",
+                         "kernel_ms": kern_ms, "traffic": traffic},
+            "rk4_steps_per_frame": sum_steps,
+            "lane_efficiency": sum_steps / sum_warp if sum_warp else None,
+            "clocks": clk.summary(),
+        }
+        line.update(extra)
+        if N == 1 and not args.no_cpu:
+            O.build()
+            t_cpu, n_cpu = cpu_frame(O, H, W)
+            line["cpu_baseline"] = {
+                "value": n_cpu / t_cpu, "unit": "rays/s", "cores": O.num_threads(), "kind": "port",
+                "sample": "one full %dx%d frame (%.1f s): oracle port of the reference's CPU path, trace on %d "
+                          "OpenMP threads, alpha lookup / remap single-threaded numpy like the reference"
+                          % (W, H, t_cpu, O.num_threads())}
+        print(json.dumps(line), flush=True)
+    if N > 1:
+        dist.destroy_process_group()
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"])
+    except Exception:
+        return 6650.0     # B200_PROFILING.md fallback
+
+
+def ncu_traffic():
+    """dram bytes per launch of the fused kernel from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
+            return json.load(f).get("lp_render_kernel", {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -198,12 +198,13 @@ def focal(image_dimension, fov):
     return (w / 2) / np.tan(hf / 2), (h / 2) / np.tan(vf / 2)
 
 
-def build_alpha_lookup(image_dimension, fov, decimals=None, psi=(0.0, 0.0)):
-    """image_lens.py:133-152 -> float32[H,W]."""
+def build_alpha_lookup(image_dimension, fov, decimals=None, psi=(0.0, 0.0), rows=None):
+    """image_lens.py:133-152 -> float32[H,W].  ``rows`` (an index array) restricts the
+    output to those frame rows (bounded CPU-baseline samples; not a reference feature)."""
     h, w = image_dimension
     fx, fy = focal(image_dimension, fov)
     xc = (np.arange(w) - w / 2) / fx
-    yc = (np.arange(h) - h / 2) / fy
+    yc = ((np.arange(h) if rows is None else np.asarray(rows)) - h / 2) / fy
     d = psi_frame(psi)[0]
     norm = np.sqrt(1.0 + xc[None, :] ** 2 + yc[:, None] ** 2)
     c = ((xc[None, :] * d[0]) + (yc[:, None] * d[1]) + d[2]) / norm
@@ -218,15 +219,20 @@ WINDING_COLORS = np.array([[0.0, 0.2, 1.0], [0.0, 0.7, 1.0], [0.0, 1.0, 0.4],
 
 
 def render_lensed_image(source, fa_lookup, winding_lookup, fov,
-                        render_loop_around=False, psi=(0.0, 0.0), return_index=False):
+                        render_loop_around=False, psi=(0.0, 0.0), return_index=False, rows=None):
     """image_lens.py:296-397 (the arguments the reference never reads —
     alpha_lookup, alpha_crit — are dropped).  With return_index=True also
     returns the int64 source index map (src_y, src_x; -1 where not sampled)."""
     H, W = source.shape[:2]
     fx, fy = focal((H, W), fov)
-    out = np.zeros_like(source)
+    if rows is None:
+        out = np.zeros_like(source)
+        yc = (np.arange(H) - H / 2) / fy
+    else:   # row subset (bounded CPU-baseline samples): lookups / output cover those rows only
+        rows = np.asarray(rows)
+        out = np.zeros((rows.size,) + source.shape[1:], dtype=source.dtype)
+        yc = (rows - H / 2) / fy
     xc = (np.arange(W) - W / 2) / fx
-    yc = (np.arange(H) - H / 2) / fy
     d, e_x, e_y, _ = psi_frame(psi)
     norm = np.sqrt(1.0 + xc[None, :] ** 2 + yc[:, None] ** 2)
     vx, vy, vz = xc[None, :] / norm, yc[:, None] / norm, 1.0 / norm
@@ -245,8 +251,8 @@ def render_lensed_image(source, fa_lookup, winding_lookup, fov,
         else:
             out[wind] = WINDING_COLORS[k]
     esc = finite & (fa_lookup <= np.pi / 2)
-    sy_map = np.full((H, W), -1, np.int64)
-    sx_map = np.full((H, W), -1, np.int64)
+    sy_map = np.full(fa_lookup.shape, -1, np.int64)
+    sx_map = np.full(fa_lookup.shape, -1, np.int64)
     if np.count_nonzero(esc):
         fa = fa_lookup[esc].astype(np.float64)
         th = theta[esc]

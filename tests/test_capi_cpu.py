@@ -1,0 +1,163 @@
+"""CPU: the C-ABI library builds (nvcc cross-compiles sm_100a without a GPU), loads, exports
+every symbol include/lightpath.h declares, and its host-side helpers agree with the reference's
+host arithmetic.  No compute calls here (they need a GPU)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "lightpath.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported(native):
+    declared = _declared_symbols()
+    assert len(declared) >= 17
+    assert set(declared) == set(native.SYMBOLS), "ctypes prototype table out of sync with lightpath.h"
+    lib = native.capi()
+    for name in declared:
+        assert hasattr(lib, name), name
+    out = subprocess.run(["nm", "-D", "--defined-only", native.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (lp_[a-z0-9_]+)", out))
+    assert set(declared) <= exported
+
+
+def test_sm100a_code_present(native):
+    out = subprocess.run(["cuobjdump", "-lelf", native.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out
+
+
+def test_abi_basics(native):
+    lib = native.capi()
+    assert lib.lp_abi_version() == 1
+    assert lib.lp_error_string(0) == b"ok"
+    assert b"invalid" in lib.lp_error_string(-1)
+    assert lib.lp_device_count() >= 0
+
+
+def test_struct_layouts(native):
+    assert ctypes.sizeof(native.lp_frame_stats) == 80
+    assert ctypes.sizeof(native.lp_camera) == 8 + 16 + 72
+    assert int(native.ext().STATS_WORDS) * 8 == ctypes.sizeof(native.lp_frame_stats)
+
+
+def test_camera_init_matches_reference_frame(native, oracle):
+    """lp_camera_init (C host helper) vs the numpy _psi_frame arithmetic (image_lens.py:38-61)."""
+    lib = native.capi()
+    from light_path_tracer_b200 import image_lens as il
+    for psi in [(0.0, 0.0), (0.1, -0.2), (np.radians(35), np.radians(50)), (np.pi / 2, 0.0), (0.0, np.pi / 2),
+                (3.0, 0.3)]:
+        cam = native.lp_camera()
+        hfov, vfov = np.radians(65.0), np.radians(40.0)
+        assert lib.lp_camera_init(1080, 1920, hfov, vfov, psi[0], psi[1], ctypes.byref(cam)) == 0
+        d, ex, ey, _ = oracle.psi_frame(psi)
+        d2, ex2, ey2, _ = il._psi_frame(psi)
+        for mine, ref, ref2 in ((cam.d, d, d2), (cam.e_x, ex, ex2), (cam.e_y, ey, ey2)):
+            assert np.allclose(list(mine), ref, rtol=0, atol=1e-15)
+            assert np.array_equal(ref, ref2)
+        fx, fy = oracle.focal((1080, 1920), (hfov, vfov))
+        assert abs(cam.fx - fx) <= 1e-12 * fx and abs(cam.fy - fy) <= 1e-12 * fy
+    assert lib.lp_camera_init(-1, 4, 1.0, 1.0, 0.0, 0.0, ctypes.byref(native.lp_camera())) == -1
+
+
+def test_no_gpu_means_error_not_fallback(native):
+    """Without a CUDA device every compute entry point must fail loudly."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    from light_path_tracer_b200.metrics import Schwarzschild
+    import pytest
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Schwarzschild(1.0).trace_ray(50.0, 0.1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        a = np.zeros(4)
+        Schwarzschild(1.0).trace_rays_batch(50.0, a, a.copy(), np.zeros(4, np.int64))
+    lib = native.capi()
+    buf = (ctypes.c_double * 4)()
+    rc = lib.lp_schw_trace_batch_f64(buf, 4, 1.0, 2.0, 50.0, 50.0, 0.05, buf, buf, None, None, None, 0, None)
+    assert rc == -2   # LP_ERR_CUDA
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under light_path_tracer_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "light_path_tracer_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "lp_oracle" not in text and "ref_harness" not in text, os.path.join(dirpath, f)
+
+
+def test_reference_api_surface():
+    """Names, positional order and defaults of the reference-facing functions."""
+    import inspect
+    from light_path_tracer_b200 import metrics, image_lens, black_hole_shadow
+
+    def params(fn):
+        return [(p.name, p.default) for p in inspect.signature(fn).parameters.values()
+                if p.kind == p.POSITIONAL_OR_KEYWORD]
+    E = inspect.Parameter.empty
+    S = metrics.Schwarzschild
+    assert params(S.__init__) == [("self", E), ("M", 1.0)]
+    assert params(S.trace_ray) == [("self", E), ("r_obs", E), ("alpha", E), ("theta", 0.0),
+                                   ("theta_obs", np.pi / 2), ("phi_max", 50.0), ("axis_refine", False)]
+    assert params(S.trace_rays_batch) == [("self", E), ("r_obs", E), ("alphas", E), ("out_fa", E), ("out_w", E)]
+    assert params(S.alpha_crit) == [("self", E), ("r_obs", E), ("theta_obs", np.pi / 2)]
+    assert params(S.initial_conditions) == [("self", E), ("r_obs", E), ("alpha", E), ("theta", 0.0),
+                                            ("theta_obs", np.pi / 2)]
+    assert params(image_lens.build_alpha_lookup) == [("image_dimension", E), ("fov", E), ("decimals", None),
+                                                     ("psi", (0.0, 0.0))]
+    assert params(image_lens.precompute_final_alpha_lookup) == [("alpha_lookup", E), ("alpha_crit", E),
+                                                                ("r_obs", E), ("metric", E)]
+    assert params(image_lens.render_lensed_image) == [
+        ("source_image", E), ("alpha_lookup", E), ("final_alpha_lookup", E), ("winding_lookup", E),
+        ("alpha_crit", E), ("fov", E), ("render_loop_around", False), ("psi", (0.0, 0.0))]
+    assert params(image_lens.pixel_to_angles) == [("pixel", E), ("image_dimension", E), ("fov", E),
+                                                  ("psi", (0.0, 0.0))]
+    assert params(image_lens.angles_to_pixel) == [("angles", E), ("image_dimension", E), ("fov", E),
+                                                  ("clip", False), ("psi", (0.0, 0.0))]
+    assert params(image_lens.main) == [("metric", None), ("M", 1.0), ("a", 0.0), ("r_obs_mult", 100.0),
+                                       ("psi", (0.0, 0.0)), ("vertical_fov_deg", 40.0)]
+    assert params(black_hole_shadow.pixel_to_viewing_angle) == [("i", E), ("n", E), ("fov", E)]
+    assert params(black_hole_shadow.get_pixel_color) == [("metric", E), ("r_obs", E), ("alpha", E),
+                                                         ("alpha_crit", E)]
+    m = S(2.0)
+    assert (m.M, m.R_S, m.R_PHOTON, m.is_spherically_symmetric) == (2.0, 4.0, 6.0, True)
+    assert m.B_CRIT == 3 * np.sqrt(3) * 2.0 and m.capture_radius() == 4.0 * 1.01
+    assert image_lens.WINDING_DTYPE is np.uint16 and image_lens.WINDING_MAX == 65535
+    assert image_lens.WINDING_COLORS.dtype == np.float32 and image_lens.WINDING_COLORS.shape == (5, 3)
+
+
+def test_scalar_helpers_golden(golden):
+    """pixel_to_angles / angles_to_pixel (host scalar helpers, image_lens.py:72-126)."""
+    from light_path_tracer_b200 import image_lens as il
+    h = golden("golden_meta.json")["frames"]["_helpers"]
+    dim, fov = (h["H"], h["W"]), tuple(h["fov"])
+    for c in h["cases"]:
+        a, th = il.pixel_to_angles(tuple(c["pixel"]), dim, fov, psi=tuple(c["psi"]))
+        assert a == c["alpha"] and th == c["theta"]
+        assert list(il.angles_to_pixel((a, th), dim, fov, psi=tuple(c["psi"]))) == c["back"]
+        assert list(il.angles_to_pixel((a * 3, th), dim, fov, clip=True, psi=tuple(c["psi"]))) == c["back_clip"]
+    assert il.angles_to_pixel((3.0, 0.0), dim, fov) == (-1, -1)
+    assert il.angles_to_pixel((3.0, 0.0), dim, fov, clip=True) == (0, 0)
+
+
+def test_host_scalars_match_reference_formulas(golden):
+    from light_path_tracer_b200.metrics import Schwarzschild
+    m = Schwarzschild(1.0)
+    assert m.alpha_crit(50.0) == 0.10200015330371326
+    assert m.alpha_crit(100.0) == 0.051461996376274736
+    g = golden("rk45_rays.npz")
+    for i in range(g["alpha"].size):
+        mm = Schwarzschild(float(g["M"][i]))
+        s0 = mm.initial_conditions(float(g["r_obs"][i]), float(g["alpha"][i]))
+        assert np.array_equal(np.array(s0), g["state0"][i])
+    # RHS freezes inside 1.001 R_S (metrics.py:766-767)
+    assert m.geodesic_equations(0.0, [0, 2.001, np.pi / 2, 0, -1, -1, 0, 3]) == [0.0] * 8

@@ -1,0 +1,76 @@
+"""CPU, gloo, world_size 2: the host-side sharding logic of the multi-GPU path
+(light_path_tracer_b200/dist.py): row-tile partition, frame round-robin, tile gather."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+
+def test_row_tiles_partition():
+    from light_path_tracer_b200.dist import row_tiles, frame_shard, sweep_grid
+    for H in (0, 1, 7, 2160, 4320, 4321):
+        for G in (1, 2, 3, 4, 8):
+            t = row_tiles(H, G)
+            assert len(t) == G and t[0][0] == 0 and sum(r for _, r in t) == H
+            assert all(t[k][0] + t[k][1] == t[k + 1][0] for k in range(G - 1))
+            assert max(r for _, r in t) - min(r for _, r in t) <= 1
+    with pytest.raises(ValueError):
+        row_tiles(10, 0)
+    all_frames = sorted(sum((frame_shard(512, r, 8) for r in range(8)), []))
+    assert all_frames == list(range(512))
+    assert len(frame_shard(512, 3, 8)) == 64
+    grid = sweep_grid()
+    assert len(grid) == 512 and grid[0][0] == 15.0 and abs(grid[-1][0] - 1000.0) < 1e-9
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, height, q):
+    import torch
+    import torch.distributed as dist
+    from light_path_tracer_b200.dist import row_tiles, gather_rows
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        row0, rows = row_tiles(height, world)[rank]
+        ok = True
+        for dtype, shape in ((torch.float32, (5, 3)), (torch.uint8, (4,)), (torch.float64, ())):
+            # the "render": every element encodes its frame row, so assembly errors show
+            tile = (torch.arange(row0, row0 + rows, dtype=torch.float64).reshape((rows,) + (1,) * len(shape))
+                    .expand((rows,) + shape) % 251).to(dtype).contiguous()
+            full = gather_rows(tile, height)
+            expect = (torch.arange(height, dtype=torch.float64).reshape((height,) + (1,) * len(shape))
+                      .expand((height,) + shape) % 251).to(dtype)
+            ok = ok and full.shape == expect.shape and torch.equal(full, expect)
+            root = gather_rows(tile, height, dst=1 % world)
+            if rank == 1 % world:
+                ok = ok and torch.equal(root, expect)
+            else:
+                ok = ok and root is None
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("height", [10, 11])
+def test_gather_rows_gloo_world2(height):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, height, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(results) == [(0, True), (1, True)]
