@@ -45,7 +45,13 @@ extern "C" {
                                      reference's order (bit-identical u, w, phi)   */
 #define LP_TRACE_FUSED      1u    /* allow FMA contraction inside the RK4 step
                                      (faster, ulp-level different trajectories)     */
-#define LP_TRACE_NO_REPACK  2u    /* disable the two-phase long-ray re-packing      */
+#define LP_TRACE_NO_REPACK  2u    /* reserved                                        */
+#define LP_TRACE_HYBRID     4u    /* FMA-contracted loop for rays that finish within 192
+                                     RK4 steps (they stay within 1e-12 of the strict
+                                     result), strict re-trace of the few longer ones
+                                     (near-critical rays, where rounding differences are
+                                     amplified): same classification and winding as
+                                     LP_TRACE_STRICT, final_alpha within 1e-9 relative  */
 
 /* ---- ray status codes (metrics.py:69, :125) ------------------------------ */
 #define LP_RAY_ESCAPED    1

@@ -36,26 +36,39 @@ __device__ __forceinline__ long long pymod(long long a, long long n)
 
 // Source direction of an escaped pixel -> pinhole plane coordinates (image_lens.py:310-352).
 // Returns front (src_vz > 1e-12) and the continuous source pixel coordinates.
+//
+// The reference normalises the pixel ray v, takes theta = arctan2(v.e_x, v.e_y) and then
+// sin(theta), cos(theta).  theta is invariant under scaling of v, and sin/cos of an arctan2
+// are the normalised components themselves, so here (st, ct) = (A, B)/hypot(A, B) with
+// A, B the dot products of the UN-normalised ray (x_cam, y_cam, 1): no arctan2, no second
+// sincos, no normalisation of v.  What has to match the reference is the INTEGER source
+// index rint(px), rint(py); the two evaluations differ by a few ulp of px (~1e-13 pixel), so
+// they can only disagree on a tie that is that close to a half-integer.
 __device__ __forceinline__ bool source_coords(const CamConsts &cam, int row, int col, float fa32,
                                               double &px, double &py)
 {
     const double xc = cam_coord(col, cam.half_w, cam.fx);
     const double yc = cam_coord(row, cam.half_h, cam.fy);
-    const double denom = __dsqrt_rn(add_(add_(1.0, mul_(xc, xc)), mul_(yc, yc)));
-    const double vx = __ddiv_rn(xc, denom), vy = __ddiv_rn(yc, denom), vz = __ddiv_rn(1.0, denom);
-    const double A = add_(add_(mul_(vx, cam.ex0), mul_(vy, cam.ex1)), mul_(vz, cam.ex2));
-    const double B = add_(add_(mul_(vx, cam.ey0), mul_(vy, cam.ey1)), mul_(vz, cam.ey2));
-    const double theta = atan2(A, B);                       // image_lens.py:314-317
-    double st, ct, sf, cf;
-    sincos(theta, &st, &ct);
+    const double A = fma(xc, cam.ex0, fma(yc, cam.ex1, cam.ex2));
+    const double B = fma(xc, cam.ey0, fma(yc, cam.ey1, cam.ey2));
+    const double n2 = fma(A, A, B * B);
+    double st = 0.0, ct = 1.0;                              // arctan2(0, 0) = 0
+    if (n2 > 0.0) {
+        const double inv = __ddiv_rn(1.0, __dsqrt_rn(n2));
+        st = A * inv; ct = B * inv;
+    }
+    double sf, cf;
     sincos((double)fa32, &sf, &cf);                         // image_lens.py:340-346
-    const double sx = add_(mul_(cf, cam.d0), mul_(sf, add_(mul_(st, cam.ex0), mul_(ct, cam.ey0))));
-    const double sy = add_(mul_(cf, cam.d1), mul_(sf, add_(mul_(st, cam.ex1), mul_(ct, cam.ey1))));
-    const double sz = add_(mul_(cf, cam.d2), mul_(sf, add_(mul_(st, cam.ex2), mul_(ct, cam.ey2))));
+    const double tx = fma(st, cam.ex0, ct * cam.ey0);
+    const double ty = fma(st, cam.ex1, ct * cam.ey1);
+    const double tz = fma(st, cam.ex2, ct * cam.ey2);
+    const double sx = fma(cf, cam.d0, sf * tx);
+    const double sy = fma(cf, cam.d1, sf * ty);
+    const double sz = fma(cf, cam.d2, sf * tz);
     const bool front = sz > 1e-12;
     if (front) {
-        px = add_(mul_(__ddiv_rn(sx, sz), cam.fx), cam.half_w);   // image_lens.py:374
-        py = add_(mul_(__ddiv_rn(sy, sz), cam.fy), cam.half_h);
+        px = fma(__ddiv_rn(sx, sz), cam.fx, cam.half_w);          // image_lens.py:374
+        py = fma(__ddiv_rn(sy, sz), cam.fy, cam.half_h);
     } else {
         px = cam.half_w;                                          // image_lens.py:356-361 (zeros * f + n/2)
         py = cam.half_h;

@@ -26,7 +26,23 @@ struct TraceArgs {
     int32_t *out_steps;     // optional
     lp_frame_stats *stats;  // optional
     int32_t row0;           // SRC_CAM: first frame row of the tile
+    int32_t retrace_steps;  // FUSED kernels: a ray that ran more RK4 steps than this is traced
+                            // again with strict arithmetic (LP_TRACE_HYBRID); INT_MAX = never
 };
+
+// LP_TRACE_HYBRID threshold.  The FMA-contracted loop differs from the strict one by ~1e-16
+// per operation; the difference grows like e^phi while a ray lingers at the photon sphere.
+// Measured (tools/fma_study.c, 2.4e7 rays over r_obs = 15..1000, dense around alpha_crit):
+// rays that finish within 275 steps agree with the strict loop to <= 3e-11 relative in
+// final_alpha with identical status and n_half_orbits; 192 (phi <= 9.6, <= 1e-12) leaves two
+// orders of margin to the 1e-9 parity bound, and in a 4K frame only ~1e-4 of the rays are
+// longer than that (they are the ones the strict retrace exists for).
+#define LP_HYBRID_RETRACE_STEPS 192
+
+static int retrace_steps_for(uint32_t flags)
+{
+    return (flags & LP_TRACE_HYBRID) ? LP_HYBRID_RETRACE_STEPS : 0x7fffffff;
+}
 
 // One ray per thread, one CTA per `blockDim.x` consecutive rays.  The grid is NOT
 // persistent on purpose: the SMSP arbiter is unfair between always-eligible warps, so a
@@ -58,6 +74,7 @@ lp_trace_kernel(const TraceArgs a, const BinetConsts c, const CamConsts cam)
             alpha = (double)a32;
         }
         binet_trace<FUSED, FAST>(c, L, alpha, r);
+        if (FUSED && r.steps > a.retrace_steps) binet_trace<false, FAST>(c, L, alpha, r);
         const double fa = (r.status == 1) ? r.fa : __longlong_as_double(0x7ff8000000000000LL);
         if (WIDE) {
             ((double *)a.out_fa)[i] = fa;                          // metrics.py:667
@@ -95,7 +112,7 @@ static int launch_trace(const TraceArgs &a, const BinetConsts &c, const CamConst
                         uint32_t flags, cudaStream_t stream)
 {
     if (a.n == 0) return LP_OK;
-    const bool fused = (flags & LP_TRACE_FUSED) != 0;
+    const bool fused = (flags & (LP_TRACE_FUSED | LP_TRACE_HYBRID)) != 0;
     const bool icmp = lp_binet_fast_ok(&c) != 0;
     const int block = trace_block_size();
     const long long chunks = (a.n + block - 1) / block;
@@ -125,6 +142,7 @@ extern "C" int lp_schw_trace_batch_f64(const double *alphas, int64_t n,
     if (rc != LP_OK) return rc;
     CamConsts cam = {};
     TraceArgs a = {};
+    a.retrace_steps = retrace_steps_for(flags);
     a.alphas = alphas; a.n = n; a.out_fa = out_fa; a.out_w = out_w;
     a.out_status = out_status; a.out_steps = out_steps; a.stats = stats;
     return launch_trace<SRC_F64, true>(a, c, cam, flags, (cudaStream_t)stream);
@@ -144,6 +162,7 @@ extern "C" int lp_schw_trace_alpha32(const float *alpha32, int64_t n,
     if (rc != LP_OK) return rc;
     CamConsts cam = {};
     TraceArgs a = {};
+    a.retrace_steps = retrace_steps_for(flags);
     a.alphas = alpha32; a.n = n; a.out_fa = out_fa32; a.out_w = out_w16;
     a.out_status = out_status; a.out_steps = out_steps; a.stats = stats;
     return launch_trace<SRC_F32, false>(a, c, cam, flags, (cudaStream_t)stream);
@@ -166,6 +185,7 @@ extern "C" int lp_schw_trace_frame(const lp_camera *h_cam, int32_t row0, int32_t
     rc = lp_make_binet_consts(M, R_S, r_obs, phi_max, h_max, &c);
     if (rc != LP_OK) return rc;
     TraceArgs a = {};
+    a.retrace_steps = retrace_steps_for(flags);
     a.n = n; a.out_fa = out_fa32; a.out_w = out_w16; a.out_alpha32 = out_alpha32;
     a.out_status = out_status; a.out_steps = out_steps; a.stats = stats; a.row0 = row0;
     return launch_trace<SRC_CAM, false>(a, c, cam, flags, (cudaStream_t)stream);
@@ -191,6 +211,7 @@ lp_render_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts c, con
         const float a32 = (float)pixel_alpha64(cam, cam_coord(col, cam.half_w, cam.fx),
                                                cam_coord(row, cam.half_h, cam.fy));
         binet_trace<FUSED, FAST>(c, L, (double)a32, r);
+        if (FUSED && r.steps > a.retrace_steps) binet_trace<false, FAST>(c, L, (double)a32, r);
         const float fa32 = (float)((r.status == 1) ? r.fa : __longlong_as_double(0x7ff8000000000000LL));
         const long long nh = r.nh < 0 ? 0 : (r.nh > 65535 ? 65535 : r.nh);
         if (a.out_fa) ((float *)a.out_fa)[i] = fa32;
@@ -209,7 +230,7 @@ template <typename T>
 static int launch_render(const TraceArgs &a, const RemapArgs &ra, const BinetConsts &c,
                          const CamConsts &cam, uint32_t flags, cudaStream_t stream)
 {
-    const bool fused = (flags & LP_TRACE_FUSED) != 0;
+    const bool fused = (flags & (LP_TRACE_FUSED | LP_TRACE_HYBRID)) != 0;
     const bool icmp = lp_binet_fast_ok(&c) != 0;
     const int block = trace_block_size();
     const long long chunks = (a.n + block - 1) / block;
@@ -245,6 +266,7 @@ extern "C" int lp_render_frame(const void *src, int32_t src_dtype, int32_t chann
     rc = lp_make_binet_consts(M, R_S, r_obs, phi_max, h_max, &c);
     if (rc != LP_OK) return rc;
     TraceArgs a = {};
+    a.retrace_steps = retrace_steps_for(flags);
     a.n = n; a.out_fa = out_fa32; a.out_w = out_w16; a.stats = stats; a.row0 = row0;
     RemapArgs ra;
     ra.src = src; ra.out = out; ra.fa32 = nullptr; ra.w16 = nullptr; ra.n = n;

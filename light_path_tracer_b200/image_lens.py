@@ -237,7 +237,7 @@ def render_lensed_image(source_image, alpha_lookup, final_alpha_lookup, winding_
 
 def render_frame(source_image, fov, r_obs, metric, psi=(0.0, 0.0), render_loop_around=False, *,
                  sampling=SAMPLE_NEAREST, rows=None, return_lookups=False, stats=None,
-                 flags=dev.TRACE_STRICT, out=None):
+                 flags=dev.TRACE_HYBRID, out=None):
     """Fully fused device-resident frame (lp_render_frame): build_alpha_lookup +
     precompute_final_alpha_lookup + render_lensed_image in ONE launch, bit-identical to
     running the three stages back to back.  ``source_image`` is a CUDA tensor [H,W(,C)];
@@ -279,7 +279,7 @@ class LensPipeline:
         self.fov = (2 * np.arctan(np.tan(vfov / 2) * self.width / self.height), vfov)  # image_lens.py:461-463
         self._t = t
 
-    def render(self, r_obs, psi=(0.0, 0.0), rows=None, stats=None, flags=dev.TRACE_STRICT, out=None):
+    def render(self, r_obs, psi=(0.0, 0.0), rows=None, stats=None, flags=dev.TRACE_HYBRID, out=None):
         return render_frame(self.src, self.fov, r_obs, self.metric, psi=psi, rows=rows, stats=stats,
                             flags=flags, out=out)
 

@@ -165,7 +165,7 @@ class Schwarzschild(Metric):
             dev.d2h_into(d_steps, steps, "steps")
 
     def trace_alpha_table(self, alpha32, r_obs, *, status=None, steps=None, stats=None,
-                          flags=dev.TRACE_STRICT):
+                          flags=dev.TRACE_HYBRID):
         """Device-resident form of image_lens.precompute_final_alpha_lookup
         (image_lens.py:155-178): float32 CUDA tensor in -> (final_alpha float32,
         winding uint16) CUDA tensors of the same shape, one launch."""

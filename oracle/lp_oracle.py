@@ -63,8 +63,12 @@ def lib():
         L.lp_oracle_shadow.restype = None
         L.lp_oracle_shadow.argtypes = [ctypes.c_int, ctypes.c_int, d, d, vp]
         L.lp_oracle_num_threads.restype = ctypes.c_int
-        if hasattr(L, "lp_oracle_rk45_trace"):
-            L.lp_oracle_rk45_trace.restype = ctypes.c_int
+        L.lp_oracle_rk45_initial_conditions.restype = ctypes.c_int
+        L.lp_oracle_rk45_initial_conditions.argtypes = [d, d, d, vp]
+        L.lp_oracle_rk45_integrate.restype = ctypes.c_int
+        L.lp_oracle_rk45_integrate.argtypes = [d, d, vp, d, d, d, d, d, d, vp, i32, vp, vp, vp, vp, vp]
+        L.lp_oracle_rk45_trace_batch.restype = None
+        L.lp_oracle_rk45_trace_batch.argtypes = [d, d, vp, i64, d, d, d, d, d, d, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -129,6 +133,57 @@ def trace_rays_batch_sin_shift(M, r_obs, alphas, sin_shift, phi_max=PHI_MAX, h_m
     lib().lp_oracle_trace_rays_batch_shift(M, 2 * M, r_obs, _p(alphas), n, int(sin_shift),
                                            phi_max, h_max, _p(fa), _p(w), _p(st))
     return fa, w, st
+
+
+# --------------------------------------------------------------------------
+# generic path: geodesic_tracer.trace_ray (scipy RK45 on the 8-D Hamiltonian), C
+# --------------------------------------------------------------------------
+RK45_DEFAULTS = dict(lambda_max=1000.0, rtol=1e-8, atol=1e-10, max_step=1.0)   # geodesic_tracer.py:22, :57-67
+
+
+def rk45_initial_conditions(M, r_obs, alpha):
+    """metrics.py:794-809 -> float64[8] or None."""
+    s0 = np.empty(8, np.float64)
+    ok = lib().lp_oracle_rk45_initial_conditions(M, r_obs, alpha, _p(s0))
+    return s0 if ok else None
+
+
+def rk45_trace_ray(M, r_obs, alpha, lambda_max=1000.0, r_stop_inner=None, r_stop_outer=None,
+                   rtol=1e-8, atol=1e-10, max_step=1.0, max_points=4096):
+    """geodesic_tracer.trace_ray (geodesic_tracer.py:74-82) -> dict(t, y[8, n], nfev, status,
+    outcome) or None for 'invalid'."""
+    s0 = rk45_initial_conditions(M, r_obs, alpha)
+    if s0 is None:
+        return None
+    r_in = 2 * M * 1.01 if r_stop_inner is None else r_stop_inner
+    r_out = s0[1] * 2.0 if r_stop_outer is None else r_stop_outer
+    traj = np.empty((max_points, 9), np.float64)
+    npts, nfev, status = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    tf = ctypes.c_double()
+    yf = np.empty(8, np.float64)
+    oc = lib().lp_oracle_rk45_integrate(M, 2 * M, _p(s0), lambda_max, rtol, atol, max_step, r_in, r_out,
+                                        _p(traj), max_points, ctypes.addressof(npts), ctypes.addressof(nfev),
+                                        ctypes.addressof(status), ctypes.addressof(tf), _p(yf))
+    n = min(int(npts.value), max_points)
+    return dict(t=traj[:n, 0].copy(), y=traj[:n, 1:].T.copy(), nfev=int(nfev.value),
+                status=int(status.value), outcome=int(oc), n_points=int(npts.value),
+                t_final=tf.value, y_final=yf, state0=s0)
+
+
+def rk45_trace_batch(M, r_obs, alphas, lambda_max=1000.0, rtol=1e-8, atol=1e-10, max_step=1.0,
+                     r_stop_inner=0.0, r_stop_outer=0.0):
+    """Batched geodesic_tracer.trace_ray -> (state f64[n,8], lambda f64[n], outcome i8[n]
+    (1/-1/0 invalid), nsteps i32[n,2] = (points, nfev), status i8[n])."""
+    alphas = np.ascontiguousarray(alphas, dtype=np.float64)
+    n = alphas.size
+    state = np.empty((n, 8), np.float64)
+    lam = np.empty(n, np.float64)
+    oc = np.empty(n, np.int8)
+    ns = np.empty((n, 2), np.int32)
+    st = np.empty(n, np.int8)
+    lib().lp_oracle_rk45_trace_batch(M, r_obs, _p(alphas), n, lambda_max, rtol, atol, max_step,
+                                     r_stop_inner, r_stop_outer, _p(state), _p(lam), _p(oc), _p(ns), _p(st))
+    return state, lam, oc, ns, st
 
 
 def precompute_final_alpha_lookup(alpha_lookup, M, r_obs, want_status=False):

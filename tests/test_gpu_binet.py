@@ -218,6 +218,49 @@ def test_fused_mode_within_tolerance(native, oracle):
     _check_batch(1.0, 100.0, alpha, fa_o, w_o, d_fa.cpu().numpy(), d_w.cpu().numpy(), "fused", oracle)
 
 
+@pytest.mark.parametrize("r_obs", [15.0, 100.0, 1000.0])
+def test_hybrid_mode_matches_strict(native, oracle, r_obs):
+    """LP_TRACE_HYBRID = FMA-contracted loop, strict re-trace of every ray longer than 192
+    steps.  Against the strict kernel on the same device: status and n_half_orbits identical
+    for EVERY ray (incl. a dense scan across the scheme's own separatrix, where only the
+    strict arithmetic reproduces the reference), final_alpha within 1e-9 relative (absolute
+    floor 1e-3 for the arccos quantisation near 0); rays longer than the
+    threshold are bit-identical because they ARE the strict result."""
+    import torch
+    m = _metrics()
+    M = 1.0
+    ac = float(oracle.alpha_crit(M, r_obs))
+    rng = np.random.default_rng(21)
+    e = 10.0 ** rng.uniform(-14, -0.5, 300000)
+    alpha = np.concatenate([
+        np.float64(np.float32(rng.uniform(0, min(8 * ac, np.pi), 1000000))),
+        ac * (1 + e * rng.choice([-1.0, 1.0], e.size)),
+        ac * (1 - 6e-8 / 5.2) * (1 + rng.normal(0, 3e-9, 200000))])
+    d_a = torch.from_numpy(alpha).cuda()
+    out = {}
+    for flags in (0, 4):
+        fa = torch.empty(alpha.size, dtype=torch.float64, device="cuda")
+        w = torch.empty(alpha.size, dtype=torch.int64, device="cuda")
+        st = torch.empty(alpha.size, dtype=torch.int8, device="cuda")
+        steps = torch.empty(alpha.size, dtype=torch.int32, device="cuda")
+        m.Schwarzschild(M).trace_rays_batch(r_obs, d_a, fa, w, status=st, steps=steps, flags=flags)
+        out[flags] = [x.cpu().numpy() for x in (fa, w, st, steps)]
+    (fa_s, w_s, st_s, n_s), (fa_h, w_h, st_h, n_h) = out[0], out[4]
+    assert np.array_equal(st_s, st_h), "classification differs for %d rays" % int((st_s != st_h).sum())
+    assert np.array_equal(w_s, w_h), "winding differs for %d rays" % int((w_s != w_h).sum())
+    esc = st_s == 1
+    # final_alpha = arccos(c) with c a double: near 0 and pi the result is quantised in steps of
+    # ulp(c)/sin(final_alpha) (SURVEY.md 7.3 H3), in the reference as much as here; two
+    # trajectories 1e-13 apart may land on adjacent quanta, so allow two of them
+    quantum = 2.0 ** -52 / np.maximum(np.sin(fa_s[esc]), 1e-300)
+    rel = np.maximum(np.abs(fa_h[esc] - fa_s[esc]) - 2 * quantum, 0.0) / np.maximum(fa_s[esc], 1e-3)
+    long_rays = n_h > 192
+    assert bits_equal(fa_s[long_rays], fa_h[long_rays]) and np.array_equal(n_s[long_rays], n_h[long_rays])
+    print("r_obs=%g: %d rays, %d escaped, %d re-traced (>192 steps), max rel diff %.2e" % (
+        r_obs, alpha.size, int(esc.sum()), int(long_rays.sum()), float(rel.max())))
+    assert rel.max() <= REL_TOL
+
+
 def test_small_final_alpha_einstein_ring(native, oracle):
     """Rays that leave almost exactly along the optical axis (final_alpha -> 0: pixels on an
     Einstein ring, and -> pi).  There arccos(-cos(heading)) is ill-conditioned and the

@@ -191,6 +191,31 @@ def test_frame_symmetry_4k(native):
     assert abs(s["sum_steps"] - 459558513) <= 5000 and s["max_steps"] >= 200
 
 
+@pytest.mark.parametrize("H,W,r_obs,psi", [(2160, 3840, 100.0, (0.0, 0.0)), (2160, 3840, 15.0, (0.05, -0.1)),
+                                           (1080, 1920, 1000.0, (0.0, 0.0))])
+def test_hybrid_frame_equals_strict_frame(native, H, W, r_obs, psi):
+    """Full-size check of the image pipeline's default arithmetic (LP_TRACE_HYBRID) against
+    LP_TRACE_STRICT (the mode that is bit-identical to the reference's trajectories): same
+    escape/capture classification and winding for every pixel, float32 final_alpha equal up
+    to a handful of one-step float32 rounding flips, rendered pixels equal wherever
+    final_alpha is."""
+    import torch
+    il = _il()
+    vfov = np.radians(40.0)
+    fov = (2 * np.arctan(np.tan(vfov / 2) * W / H), vfov)
+    metric = _metric(1.0)
+    src = torch.rand(H, W, 3, device="cuda")
+    out_s, fa_s, w_s = il.render_frame(src, fov, r_obs, metric, psi=psi, flags=0, return_lookups=True)
+    out_h, fa_h, w_h = il.render_frame(src, fov, r_obs, metric, psi=psi, flags=4, return_lookups=True)
+    assert torch.equal(torch.isnan(fa_s), torch.isnan(fa_h))
+    assert torch.equal(w_s.view(torch.int16), w_h.view(torch.int16))
+    d = (fa_s.view(torch.int32) - fa_h.view(torch.int32)).abs()
+    d[torch.isnan(fa_s)] = 0
+    assert int(d.max()) <= 1 and int((d > 0).sum()) <= 16
+    same = d == 0
+    assert torch.equal(out_s[same], out_h[same])
+
+
 def test_shadow_golden(native, golden):
     from light_path_tracer_b200 import black_hole_shadow as bs
     g = golden("shadow.npz")
