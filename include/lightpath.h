@@ -206,13 +206,19 @@ int lp_frame_stats_reduce(const float *fa32, const uint16_t *w16,
 /* Replaces geodesic_tracer.trace_ray / integrate_geodesic (geodesic_tracer.py:22-82)
  * for a Schwarzschild metric, batched over viewing angles: initial conditions as
  * metrics.py:794-809, RHS as metrics.py:763-790, Dormand-Prince 5(4) with scipy's
- * step controller (rtol, atol, max_step, first-step selection), terminal events at
- * r_stop_inner (falling) / r_stop_outer (rising) located on the quartic dense
- * output, outcome = captured if r_final <= 1.1*r_stop_inner.
+ * step controller (rtol, atol, max_step, first-step selection — the reference calls
+ * solve_ivp(method='RK45', max_step=1.0, rtol=1e-8, atol=1e-10, dense_output=True),
+ * geodesic_tracer.py:57-67), terminal events at r_stop_inner (falling) / r_stop_outer
+ * (rising) located with brentq on the quartic dense output, outcome = captured if
+ * r_final <= 1.1*r_stop_inner (geodesic_tracer.py:69-70).
  *   out_state  : [n][8] final state (t, r, theta, phi, p_t, p_r, p_theta, p_phi)
- *   out_lambda : [n] final affine parameter
- *   out_outcome: [n] 1 escaped / -1 captured / 0 invalid (initial_conditions -> None)
- *   out_nsteps : [n][2] accepted steps, RHS evaluations (optional)
+ *                = OdeResult.y[:, -1]; NaN for invalid rays
+ *   out_lambda : [n] final affine parameter = OdeResult.t[-1]
+ *   out_outcome: [n] 1 escaped / -1 captured / 0 invalid (initial_conditions -> None,
+ *                geodesic_tracer.py:79-81)
+ *   out_nsteps : [n][2] optional: len(OdeResult.t) (1 + accepted steps), OdeResult.nfev
+ *   out_status : [n] optional: OdeResult.status (1 event, 0 reached lambda_max,
+ *                -1 step size too small), -2 for invalid rays
  * r_stop_inner / r_stop_outer <= 0 select the reference's defaults
  * (capture_radius() = 1.01 R_S, 2*r_obs). */
 int lp_schw_rk45_trace_batch(const double *alphas, int64_t n,
@@ -220,16 +226,36 @@ int lp_schw_rk45_trace_batch(const double *alphas, int64_t n,
                              double lambda_max, double rtol, double atol, double max_step,
                              double r_stop_inner, double r_stop_outer,
                              double *out_state, double *out_lambda,
-                             int8_t *out_outcome, int32_t *out_nsteps, void *stream);
+                             int8_t *out_outcome, int32_t *out_nsteps, int8_t *out_status,
+                             void *stream);
 
-/* Single-ray variant that also records the accepted-step trajectory (what
- * OdeResult.t / .y hold, geodesic_tracer.py:57-67): traj is [max_points][9]
- * (lambda, state[8]); *n_points (device int32) receives the count. */
-int lp_schw_rk45_trace_path(double alpha, double M, double R_S, double r_obs,
-                            double lambda_max, double rtol, double atol, double max_step,
-                            double r_stop_inner, double r_stop_outer,
-                            double *traj, int32_t max_points, int32_t *n_points,
-                            int8_t *out_outcome, int32_t *out_nfev, void *stream);
+/* Same, also recording every accepted point (what OdeResult.t / .y hold and
+ * main.py:30-31 / plot_trajectories, geodesic_tracer.py:89-142, read):
+ * traj is [n][max_points][9] rows (lambda, state[8]); n_points[i] receives
+ * len(OdeResult.t) of ray i (rows beyond max_points are dropped, the count is not
+ * clipped).  The last row is the event point. */
+int lp_schw_rk45_trace_paths(const double *alphas, int64_t n,
+                             double M, double R_S, double r_obs,
+                             double lambda_max, double rtol, double atol, double max_step,
+                             double r_stop_inner, double r_stop_outer,
+                             double *traj, int32_t max_points, int32_t *n_points,
+                             double *out_state, double *out_lambda,
+                             int8_t *out_outcome, int32_t *out_nsteps, int8_t *out_status,
+                             void *stream);
+
+/* integrate_geodesic(metric, state0, lambda_max, r_stop_inner, r_stop_outer)
+ * (geodesic_tracer.py:22-71) for explicit initial states: state0 is [n][8]
+ * (t, r, theta, phi, p_t, p_r, p_theta, p_phi), not necessarily equatorial or null.
+ * traj / n_points may be NULL (no trajectory).  r_stop_outer <= 0 -> 2*state0[1]
+ * per ray (geodesic_tracer.py:44-45). */
+int lp_schw_rk45_integrate_paths(const double *state0, int64_t n,
+                                 double M, double R_S,
+                                 double lambda_max, double rtol, double atol, double max_step,
+                                 double r_stop_inner, double r_stop_outer,
+                                 double *traj, int32_t max_points, int32_t *n_points,
+                                 double *out_state, double *out_lambda,
+                                 int8_t *out_outcome, int32_t *out_nsteps, int8_t *out_status,
+                                 void *stream);
 
 /* ---- measurement helpers --------------------------------------------------- */
 

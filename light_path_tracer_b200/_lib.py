@@ -60,9 +60,11 @@ SYMBOLS = {
     "lp_frame_stats_reset": (ctypes.c_int, [_VP, _VP]),
     "lp_frame_stats_reduce": (ctypes.c_int, [_VP, _VP, _VP, _VP, _I64, _VP, _VP]),
     "lp_schw_rk45_trace_batch": (ctypes.c_int, [_VP, _I64, _D, _D, _D, _D, _D, _D, _D, _D, _D,
-                                                _VP, _VP, _VP, _VP, _VP]),
-    "lp_schw_rk45_trace_path": (ctypes.c_int, [_D, _D, _D, _D, _D, _D, _D, _D, _D, _D, _VP, _I32,
-                                               _VP, _VP, _VP, _VP]),
+                                                _VP, _VP, _VP, _VP, _VP, _VP]),
+    "lp_schw_rk45_trace_paths": (ctypes.c_int, [_VP, _I64, _D, _D, _D, _D, _D, _D, _D, _D, _D, _VP, _I32,
+                                                _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "lp_schw_rk45_integrate_paths": (ctypes.c_int, [_VP, _I64, _D, _D, _D, _D, _D, _D, _D, _D, _VP, _I32,
+                                                    _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "lp_bench_dfma": (ctypes.c_int, [_I32, _I32, _I32, _VP, _VP]),
 }
 

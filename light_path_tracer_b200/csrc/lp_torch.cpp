@@ -191,7 +191,7 @@ void stats_reduce(const Tensor &fa32, OptTensor w16, OptTensor status, OptTensor
 
 void rk45_trace_batch(const Tensor &alphas, double M, double R_S, double r_obs, double lambda_max, double rtol,
                       double atol, double max_step, double r_in, double r_out, Tensor out_state, Tensor out_lambda,
-                      Tensor out_outcome, OptTensor out_nsteps)
+                      Tensor out_outcome, OptTensor out_nsteps, OptTensor out_status)
 {
     const int64_t n = alphas.numel();
     c10::cuda::CUDAGuard g(alphas.device());
@@ -201,22 +201,50 @@ void rk45_trace_batch(const Tensor &alphas, double M, double R_S, double r_obs, 
                                    (double *)ptr(out_lambda, c10::ScalarType::Double, "out_lambda", n),
                                    (int8_t *)ptr(out_outcome, c10::ScalarType::Char, "out_outcome", n),
                                    (int32_t *)optptr(out_nsteps, c10::ScalarType::Int, "out_nsteps", 2 * n),
+                                   (int8_t *)optptr(out_status, c10::ScalarType::Char, "out_status", n),
                                    stream_of(alphas)),
           "lp_schw_rk45_trace_batch");
 }
 
-void rk45_trace_path(double alpha, double M, double R_S, double r_obs, double lambda_max, double rtol, double atol,
-                     double max_step, double r_in, double r_out, Tensor traj, Tensor n_points, Tensor outcome,
-                     Tensor nfev)
+void rk45_trace_paths(const Tensor &alphas, double M, double R_S, double r_obs, double lambda_max, double rtol,
+                      double atol, double max_step, double r_in, double r_out, Tensor traj, int64_t max_points,
+                      Tensor n_points, Tensor out_state, Tensor out_lambda, Tensor out_outcome, Tensor out_nsteps,
+                      Tensor out_status)
 {
-    const int64_t max_points = traj.numel() / 9;
-    c10::cuda::CUDAGuard g(traj.device());
-    check(lp_schw_rk45_trace_path(alpha, M, R_S, r_obs, lambda_max, rtol, atol, max_step, r_in, r_out,
-                                  (double *)ptr(traj, c10::ScalarType::Double, "traj", 9),
-                                  (int32_t)max_points, (int32_t *)ptr(n_points, c10::ScalarType::Int, "n_points", 1),
-                                  (int8_t *)ptr(outcome, c10::ScalarType::Char, "outcome", 1),
-                                  (int32_t *)ptr(nfev, c10::ScalarType::Int, "nfev", 1), stream_of(traj)),
-          "lp_schw_rk45_trace_path");
+    const int64_t n = alphas.numel();
+    c10::cuda::CUDAGuard g(alphas.device());
+    check(lp_schw_rk45_trace_paths((const double *)ptr(alphas, c10::ScalarType::Double, "alphas", 0), n, M, R_S, r_obs,
+                                   lambda_max, rtol, atol, max_step, r_in, r_out,
+                                   (double *)ptr(traj, c10::ScalarType::Double, "traj", n * max_points * 9),
+                                   (int32_t)max_points, (int32_t *)ptr(n_points, c10::ScalarType::Int, "n_points", n),
+                                   (double *)ptr(out_state, c10::ScalarType::Double, "out_state", 8 * n),
+                                   (double *)ptr(out_lambda, c10::ScalarType::Double, "out_lambda", n),
+                                   (int8_t *)ptr(out_outcome, c10::ScalarType::Char, "out_outcome", n),
+                                   (int32_t *)ptr(out_nsteps, c10::ScalarType::Int, "out_nsteps", 2 * n),
+                                   (int8_t *)ptr(out_status, c10::ScalarType::Char, "out_status", n),
+                                   stream_of(alphas)),
+          "lp_schw_rk45_trace_paths");
+}
+
+void rk45_integrate_paths(const Tensor &state0, double M, double R_S, double lambda_max, double rtol, double atol,
+                          double max_step, double r_in, double r_out, OptTensor traj, int64_t max_points,
+                          OptTensor n_points, Tensor out_state, Tensor out_lambda, Tensor out_outcome,
+                          Tensor out_nsteps, Tensor out_status)
+{
+    const int64_t n = state0.numel() / 8;
+    c10::cuda::CUDAGuard g(state0.device());
+    check(lp_schw_rk45_integrate_paths((const double *)ptr(state0, c10::ScalarType::Double, "state0", 0), n, M, R_S,
+                                       lambda_max, rtol, atol, max_step, r_in, r_out,
+                                       (double *)optptr(traj, c10::ScalarType::Double, "traj", n * max_points * 9),
+                                       (int32_t)max_points,
+                                       (int32_t *)optptr(n_points, c10::ScalarType::Int, "n_points", n),
+                                       (double *)ptr(out_state, c10::ScalarType::Double, "out_state", 8 * n),
+                                       (double *)ptr(out_lambda, c10::ScalarType::Double, "out_lambda", n),
+                                       (int8_t *)ptr(out_outcome, c10::ScalarType::Char, "out_outcome", n),
+                                       (int32_t *)ptr(out_nsteps, c10::ScalarType::Int, "out_nsteps", 2 * n),
+                                       (int8_t *)ptr(out_status, c10::ScalarType::Char, "out_status", n),
+                                       stream_of(state0)),
+          "lp_schw_rk45_integrate_paths");
 }
 
 void bench_dfma(int64_t blocks, int64_t threads, int64_t iters, Tensor sink)
@@ -257,6 +285,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.def("stats_reset", &stats_reset);
     m.def("stats_reduce", &stats_reduce);
     m.def("rk45_trace_batch", &rk45_trace_batch);
-    m.def("rk45_trace_path", &rk45_trace_path);
+    m.def("rk45_trace_paths", &rk45_trace_paths);
+    m.def("rk45_integrate_paths", &rk45_integrate_paths);
     m.def("bench_dfma", &bench_dfma);
 }

@@ -1,0 +1,230 @@
+"""Generic geodesic integrator — drop-in for the reference's ``geodesic_tracer`` module
+(reference: geodesic_tracer.py:22-142) on Schwarzschild metrics.
+
+``integrate_geodesic`` / ``trace_ray`` keep the reference's signatures and return
+``(solution, outcome)`` with ``solution`` shaped like scipy's ``OdeResult`` (``.t``,
+``.y`` [8, n_points], ``.t_events``, ``.y_events``, ``.nfev``, ``.status`` ...).  The
+integration — scipy's RK45 controller, events and dense-output root finding — runs in the
+CUDA kernel lp_rk45_kernel (csrc/lp_rk45.cu) through lp_schw_rk45_* (include/lightpath.h);
+no scipy, no CPU fallback.
+
+Beyond the reference API: ``trace_rays`` (batched, device resident — BASELINE config 3's
+"full-frame" form of trace_ray) and ``trace_paths`` (several trajectories in one launch,
+what ``plot_trajectories`` needs).
+"""
+import numpy as np
+
+from . import _device as dev
+from . import _lib
+from .metrics import Schwarzschild
+
+# solve_ivp arguments hard-coded by the reference (geodesic_tracer.py:57-67)
+RTOL, ATOL, MAX_STEP = 1e-8, 1e-10, 1.0
+_MESSAGES = {0: "The solver successfully reached the end of the integration interval.",
+             1: "A termination event occurred.",
+             -1: "Required step size is less than spacing between numbers."}
+_OUTCOME = {1: "escaped", -1: "captured", 0: "invalid"}
+
+
+class OdeResult(dict):
+    """Attribute-access result bunch with the fields of scipy.integrate.OdeResult that the
+    reference's callers read.  ``sol`` (the dense-output callable) is not materialised: the
+    kernel uses the dense output internally for event location only."""
+
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError as e:
+            raise AttributeError(name) from e
+
+
+def _require_schwarzschild(metric):
+    if not isinstance(metric, Schwarzschild):
+        raise NotImplementedError(
+            "the CUDA generic integrator carries the Schwarzschild right-hand side "
+            "(metrics.py:763-790); %s is not supported" % type(metric).__name__)
+
+
+def _alloc(t, n, device):
+    return (t.empty((n, 8), dtype=t.float64, device=device), t.empty(n, dtype=t.float64, device=device),
+            t.empty(n, dtype=t.int8, device=device), t.empty((n, 2), dtype=t.int32, device=device),
+            t.empty(n, dtype=t.int8, device=device))
+
+
+def _paths(metric, alphas=None, state0=None, r_obs=None, lambda_max=1000.0, r_stop_inner=None,
+           r_stop_outer=None, max_points=0):
+    """Run the kernel with trajectory recording; grows the trajectory buffer if a ray has
+    more accepted points than expected.  Returns host arrays."""
+    t = dev.torch()
+    e = _lib.ext()
+    _require_schwarzschild(metric)
+    r_in = float(metric.capture_radius() if r_stop_inner is None else r_stop_inner)
+    r_out = float(0.0 if r_stop_outer is None else r_stop_outer)
+    if r_stop_outer is not None and not r_out > 0.0:
+        raise ValueError("r_stop_outer must be positive")
+    src = np.ascontiguousarray(alphas if state0 is None else state0, dtype=np.float64)
+    n = src.size if state0 is None else src.shape[0]
+    d_in = dev.h2d(src.reshape(-1), "rk45_in")
+    state, lam, outcome, nsteps, status = _alloc(t, n, d_in.device)
+    cap = int(max_points) if max_points else int(min(4096, 2 * lambda_max / MAX_STEP + 64))
+    while True:
+        traj = t.empty((n, cap, 9), dtype=t.float64, device=d_in.device)
+        npts = t.empty(n, dtype=t.int32, device=d_in.device)
+        if state0 is None:
+            e.rk45_trace_paths(d_in, float(metric.M), float(metric.R_S), float(r_obs), float(lambda_max),
+                               RTOL, ATOL, MAX_STEP, r_in, r_out, traj, cap, npts, state, lam, outcome,
+                               nsteps, status)
+        else:
+            e.rk45_integrate_paths(d_in, float(metric.M), float(metric.R_S), float(lambda_max), RTOL, ATOL,
+                                   MAX_STEP, r_in, r_out, traj, cap, npts, state, lam, outcome, nsteps, status)
+        need = int(npts.max().item()) if n else 0
+        if need <= cap or max_points:
+            break
+        cap = need
+    return (traj.cpu().numpy(), npts.cpu().numpy(), state.cpu().numpy(), lam.cpu().numpy(),
+            outcome.cpu().numpy(), nsteps.cpu().numpy(), status.cpu().numpy(), r_in, r_out)
+
+
+def _solution(traj, n_points, state, lam, nsteps, status, r_in, r_out_used):
+    n = int(n_points)
+    ts = traj[:n, 0].copy()
+    ys = traj[:n, 1:].T.copy()
+    st = int(status)
+    t_events = [np.empty(0), np.empty(0)]
+    y_events = [np.empty(0), np.empty(0)]
+    if st == 1:
+        # which terminal event fired: the one whose radius the event point sits on
+        k = 0 if abs(state[1] - r_in) <= abs(state[1] - r_out_used) else 1
+        t_events[k] = np.array([lam])
+        y_events[k] = state[None, :].copy()
+    return OdeResult(t=ts, y=ys, sol=None, t_events=t_events, y_events=y_events, nfev=int(nsteps[1]),
+                     njev=0, nlu=0, status=st, message=_MESSAGES.get(st, ""), success=st >= 0)
+
+
+def integrate_geodesic(metric, state0, lambda_max=1000.0, r_stop_inner=None, r_stop_outer=None):
+    """Integrate the geodesic equations from an explicit 8-D initial state
+    (geodesic_tracer.py:22-71).  Returns ``(solution, 'captured' | 'escaped')``."""
+    s0 = np.asarray(state0, dtype=np.float64).reshape(1, 8)
+    traj, npts, state, lam, outcome, nsteps, status, r_in, r_out = _paths(
+        metric, state0=s0, lambda_max=lambda_max, r_stop_inner=r_stop_inner, r_stop_outer=r_stop_outer)
+    r_out_used = r_out if r_out > 0.0 else float(s0[0, 1]) * 2.0
+    sol = _solution(traj[0], npts[0], state[0], lam[0], nsteps[0], status[0], r_in, r_out_used)
+    return sol, _OUTCOME[int(outcome[0])]
+
+
+def trace_ray(metric, r_obs, alpha, **kwargs):
+    """Trace a single ray from its viewing angle with the full Hamiltonian
+    (geodesic_tracer.py:74-82).  Returns ``(solution, outcome)`` or ``(None, 'invalid')``."""
+    state0 = metric.initial_conditions(r_obs, alpha)
+    if state0 is None:
+        return None, 'invalid'
+    return integrate_geodesic(metric, state0, **kwargs)
+
+
+def trace_paths(metric, r_obs, alphas, lambda_max=1000.0, r_stop_inner=None, r_stop_outer=None):
+    """``[trace_ray(metric, r_obs, a) for a in alphas]`` in one launch (initial conditions
+    evaluated on the device)."""
+    alphas = np.atleast_1d(np.asarray(alphas, dtype=np.float64))
+    traj, npts, state, lam, outcome, nsteps, status, r_in, r_out = _paths(
+        metric, alphas=alphas, r_obs=r_obs, lambda_max=lambda_max, r_stop_inner=r_stop_inner,
+        r_stop_outer=r_stop_outer)
+    r_out_used = r_out if r_out > 0.0 else float(r_obs) * 2.0
+    res = []
+    for i in range(alphas.size):
+        if outcome[i] == 0:
+            res.append((None, 'invalid'))
+        else:
+            res.append((_solution(traj[i], npts[i], state[i], lam[i], nsteps[i], status[i], r_in, r_out_used),
+                        _OUTCOME[int(outcome[i])]))
+    return res
+
+
+def trace_rays(metric, r_obs, alphas, lambda_max=1000.0, r_stop_inner=None, r_stop_outer=None, *,
+               return_status=False):
+    """Batched ``trace_ray`` without trajectories: what ``solution.y[:, -1]``, ``solution.t[-1]``
+    and ``outcome`` would be for every viewing angle.
+
+    ``alphas``: numpy array or CUDA float64 tensor (any shape).  Returns ``(state [..., 8],
+    lambda [...], outcome int8 [...] (1 escaped / -1 captured / 0 invalid), nsteps int32
+    [..., 2] = (len(solution.t), solution.nfev))`` — CUDA tensors for tensor input, numpy
+    arrays otherwise."""
+    t = dev.torch()
+    e = _lib.ext()
+    _require_schwarzschild(metric)
+    tensor_in = type(alphas).__module__.startswith("torch")
+    if tensor_in:
+        d_a = alphas.contiguous().reshape(-1)
+        shape = tuple(alphas.shape)
+    else:
+        a_np = np.ascontiguousarray(alphas, dtype=np.float64)
+        shape = a_np.shape
+        d_a = dev.h2d(a_np.reshape(-1), "rk45_in") if a_np.size else t.empty(0, dtype=t.float64, device=dev.device())
+    n = d_a.numel()
+    state, lam, outcome, nsteps, status = _alloc(t, n, d_a.device)
+    r_in = float(metric.capture_radius() if r_stop_inner is None else r_stop_inner)
+    r_out = float(0.0 if r_stop_outer is None else r_stop_outer)
+    if n:
+        e.rk45_trace_batch(d_a, float(metric.M), float(metric.R_S), float(r_obs), float(lambda_max), RTOL, ATOL,
+                           MAX_STEP, r_in, r_out, state, lam, outcome, nsteps, status)
+    out = (state.reshape(shape + (8,)), lam.reshape(shape), outcome.reshape(shape), nsteps.reshape(shape + (2,)))
+    if return_status:
+        out = out + (status.reshape(shape),)
+    if tensor_in:
+        return out
+    return tuple(x.cpu().numpy() for x in out)
+
+
+def plot_trajectories(metric, r_obs, angles_deg, ax=None):
+    """Plot photon trajectories for several viewing angles (geodesic_tracer.py:89-142); the
+    rays are traced in one launch.  Needs matplotlib (drawing only)."""
+    import matplotlib.pyplot as plt
+    if ax is None:
+        _, ax = plt.subplots(figsize=(10, 10))
+    theta = np.linspace(0, 2 * np.pi, 200)
+    r_horizon = metric.capture_radius()
+    ax.fill(r_horizon * np.cos(theta), r_horizon * np.sin(theta), 'k', label='Event horizon')
+    if hasattr(metric, 'R_PHOTON'):
+        ax.plot(metric.R_PHOTON * np.cos(theta), metric.R_PHOTON * np.sin(theta), 'r--', linewidth=1.5,
+                label='Photon sphere')
+    ax.plot(r_obs, 0, 'go', markersize=10, label=f'Observer (r={r_obs}M)')
+    for alpha_deg, (solution, outcome) in zip(angles_deg, trace_paths(metric, r_obs, np.radians(angles_deg))):
+        if solution is None:
+            continue
+        r, phi = solution.y[1], solution.y[3]
+        escaped = outcome == 'escaped'
+        ax.plot(r * np.cos(phi), r * np.sin(phi), color='steelblue' if escaped else 'crimson',
+                linestyle='-' if escaped else '--', linewidth=1.2, label=f'α={alpha_deg}° ({outcome})')
+    ax.set_title(f'Photon trajectories (critical angle ≈ {np.degrees(metric.alpha_crit(r_obs)):.2f}°)')
+    ax.set_xlabel('x / M')
+    ax.set_ylabel('y / M')
+    ax.set_aspect('equal')
+    ax.legend(loc='upper left', fontsize=8)
+    ax.grid(True, alpha=0.3)
+    return ax
+
+
+def outcome_table(metric, r_obs, angles_deg):
+    """The alpha -> b -> CAPTURED/ESCAPED table the reference prints from ``__main__``
+    (geodesic_tracer.py:164-172) -> [(alpha_deg, b, 'CAPTURED' | 'ESCAPED')]."""
+    rows = []
+    for alpha_deg, (_, outcome) in zip(angles_deg, trace_paths(metric, r_obs, np.radians(angles_deg))):
+        b = metric.viewing_angle_to_impact_parameter(np.radians(alpha_deg), r_obs)
+        rows.append((alpha_deg, float(b), "CAPTURED" if outcome == 'captured' else "ESCAPED"))
+    return rows
+
+
+if __name__ == '__main__':
+    metric = Schwarzschild(M=1.0)
+    r_obs = 50.0 * metric.M
+    angles = [0, 2, 4, 5, 5.5, 5.97, 6.5, 8, 10, 15]
+    print("=" * 60)
+    print("Geodesic Tracer")
+    print("=" * 60)
+    print(f"Metric: {type(metric).__name__}")
+    print(f"Observer radius: r_obs = {r_obs} M")
+    print(f"Critical viewing angle: {np.degrees(metric.alpha_crit(r_obs)):.4f}°")
+    print("=" * 60)
+    print("\nTracing rays:")
+    print("-" * 40)
+    for alpha_deg, b, status in outcome_table(metric, r_obs, angles):
+        print(f"  α = {alpha_deg:6.2f}°  →  b = {b:6.3f} M  →  {status}")

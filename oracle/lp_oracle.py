@@ -149,10 +149,14 @@ def rk45_initial_conditions(M, r_obs, alpha):
 
 
 def rk45_trace_ray(M, r_obs, alpha, lambda_max=1000.0, r_stop_inner=None, r_stop_outer=None,
-                   rtol=1e-8, atol=1e-10, max_step=1.0, max_points=4096):
+                   rtol=1e-8, atol=1e-10, max_step=1.0, max_points=4096, state0=None):
     """geodesic_tracer.trace_ray (geodesic_tracer.py:74-82) -> dict(t, y[8, n], nfev, status,
-    outcome) or None for 'invalid'."""
-    s0 = rk45_initial_conditions(M, r_obs, alpha)
+    outcome) or None for 'invalid'.  With ``state0`` (8 values): integrate_geodesic
+    (geodesic_tracer.py:22-71) from that explicit state instead."""
+    if state0 is not None:
+        s0 = np.ascontiguousarray(state0, dtype=np.float64).copy()
+    else:
+        s0 = rk45_initial_conditions(M, r_obs, alpha)
     if s0 is None:
         return None
     r_in = 2 * M * 1.01 if r_stop_inner is None else r_stop_inner

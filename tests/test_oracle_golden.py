@@ -89,3 +89,34 @@ def test_alpha_crit(oracle):
     # SURVEY.md Appendix A
     assert oracle.alpha_crit(1.0, 50.0) == 0.10200015330371326
     assert oracle.alpha_crit(1.0, 100.0) == 0.051461996376274736
+
+
+def test_rk45_golden_rays(oracle, golden):
+    """The scipy-RK45 restatement (oracle/lp_oracle_rk45.c) against the reference's
+    geodesic_tracer.trace_ray (scipy 1.18.1): accepted points and nfev EXACT for all 30 rays
+    (i.e. the whole accept/reject sequence and the event step are reproduced), event point and
+    final state to 1e-11, every accepted point of the trajectory to 1e-8."""
+    g = golden("rk45_rays.npz")
+    off = g["traj_offsets"]
+    for i in range(g["alpha"].size):
+        r = oracle.rk45_trace_ray(float(g["M"][i]), float(g["r_obs"][i]), float(g["alpha"][i]))
+        assert r["outcome"] == g["outcome"][i] and r["status"] == g["status"][i]
+        assert r["n_points"] == g["n_points"][i] and r["nfev"] == g["nfev"][i], i
+        assert np.array_equal(r["state0"], g["state0"][i])
+        assert abs(r["t_final"] - g["t_final"][i]) <= 1e-11 * max(1.0, g["t_final"][i])
+        assert (np.abs(r["y_final"] - g["y_final"][i]) <= 1e-11 * np.maximum(np.abs(g["y_final"][i]), 1e-3)).all()
+        sl = slice(off[i], off[i + 1])
+        assert np.abs(r["t"] - g["traj_t"][sl]).max() <= 1e-8
+        assert (np.abs(r["y"][1] - g["traj_r"][sl]) / g["traj_r"][sl]).max() <= 1e-8
+        assert np.abs(r["y"][3] - g["traj_phi"][sl]).max() <= 1e-8
+
+
+def test_rk45_batch_matches_single(oracle):
+    rng = np.random.default_rng(4)
+    alpha = np.concatenate([rng.uniform(0, 3.1, 200), [0.0, np.nan]])
+    state, lam, oc, ns, st = oracle.rk45_trace_batch(1.0, 60.0, alpha)
+    for i in (0, 17, 101, 200):
+        r = oracle.rk45_trace_ray(1.0, 60.0, float(alpha[i]))
+        assert np.array_equal(state[i], r["y_final"]) and lam[i] == r["t_final"] and oc[i] == r["outcome"]
+        assert tuple(ns[i]) == (r["n_points"], r["nfev"]) and st[i] == r["status"]
+    assert oc[-1] == 0 and np.isnan(state[-1]).all() and st[-1] == -2
