@@ -113,6 +113,12 @@ int         lp_device_props(int32_t *sm_count, int32_t *clock_khz);
 int lp_camera_init(int32_t height, int32_t width, double hfov, double vfov,
                    double psi_y, double psi_x, lp_camera *h_cam);
 
+/* Diagnostics: whether the kernels may form the pixel coordinates (i - n/2)/f
+ * (image_lens.py:141-142) with a multiplication by RN(1/f) and two fused corrections
+ * instead of a division.  The library checks, per call, that this is bit-identical to
+ * the division for every column / row of the frame and otherwise divides. */
+int lp_camera_fast_coords(const lp_camera *h_cam, int32_t *fast_x, int32_t *fast_y);
+
 /* ---- kernel (1a): Schwarzschild Binet-equation RK4 tracer ---------------- */
 
 /* Replaces Schwarzschild.trace_rays_batch / _trace_rays_batch_schwarzschild

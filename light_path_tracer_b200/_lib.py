@@ -46,6 +46,7 @@ SYMBOLS = {
     "lp_device_count": (ctypes.c_int, []),
     "lp_device_props": (ctypes.c_int, [_VP, _VP]),
     "lp_camera_init": (ctypes.c_int, [_I32, _I32, _D, _D, _D, _D, _CAMP]),
+    "lp_camera_fast_coords": (ctypes.c_int, [_CAMP, _VP, _VP]),
     "lp_schw_trace_batch_f64": (ctypes.c_int, [_VP, _I64, _D, _D, _D, _D, _D, _VP, _VP, _VP, _VP,
                                                _VP, _U32, _VP]),
     "lp_schw_trace_alpha32": (ctypes.c_int, [_VP, _I64, _D, _D, _D, _D, _D, _VP, _VP, _VP, _VP,

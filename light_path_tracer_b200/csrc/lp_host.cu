@@ -78,6 +78,8 @@ int lp_make_binet_consts(double M, double R_S, double r_obs, double phi_max, dou
     c->uc = 1.0 / (R_S * 1.01);
     c->ue = 1.0 / (2.0 * r_obs);
     c->cap_r = R_S * 1.1;
+    c->r_esc = 1.0 / c->ue;
+    c->ue_sq = c->ue * c->ue;
 
     // replay the phi bookkeeping of the while-loop (metrics.py:72-78, :93, :115)
     int shift = 0;
@@ -127,6 +129,21 @@ int lp_binet_fast_ok(const BinetConsts *c)
     return hc > he + 1u;
 }
 
+// 1 when the multiply + two-fma form of (i - half) / f used by cam_coord() equals the IEEE
+// division bit for bit for every i in [0, n) (it always should, by Markstein's theorem, as long
+// as inv_f = RN(1/f); this makes it a checked fact per frame rather than a proof obligation).
+static int coord_div_is_exact(int n, double half, double f, double inv_f)
+{
+    if (!(f > 0.0) || !isfinite(f) || !isfinite(inv_f)) return 0;
+    for (int i = 0; i < n; ++i) {
+        const double x = (double)i - half;
+        const double q = x * inv_f;
+        const double q2 = fma(fma(-q, f, x), inv_f, q);
+        if (q2 != x / f) return 0;
+    }
+    return 1;
+}
+
 int lp_make_cam_consts(const lp_camera *cam, CamConsts *o)
 {
     if (!cam || cam->height < 0 || cam->width < 0) return LP_ERR_INVALID_ARG;
@@ -139,6 +156,10 @@ int lp_make_cam_consts(const lp_camera *cam, CamConsts *o)
     o->d0 = cam->d[0]; o->d1 = cam->d[1]; o->d2 = cam->d[2];
     o->ex0 = cam->e_x[0]; o->ex1 = cam->e_x[1]; o->ex2 = cam->e_x[2];
     o->ey0 = cam->e_y[0]; o->ey1 = cam->e_y[1]; o->ey2 = cam->e_y[2];
+    o->inv_fx = 1.0 / o->fx;
+    o->inv_fy = 1.0 / o->fy;
+    o->fast_x = coord_div_is_exact(o->width, o->half_w, o->fx, o->inv_fx);
+    o->fast_y = coord_div_is_exact(o->height, o->half_h, o->fy, o->inv_fy);
     return LP_OK;
 }
 
@@ -180,5 +201,15 @@ extern "C" int lp_camera_init(int32_t height, int32_t width, double hfov, double
     }
     n = n > 1e-12 ? n : 1e-12;
     for (int i = 0; i < 3; ++i) ey[i] /= n;
+    return LP_OK;
+}
+
+extern "C" int lp_camera_fast_coords(const lp_camera *cam, int32_t *fast_x, int32_t *fast_y)
+{
+    CamConsts c;
+    const int rc = lp_make_cam_consts(cam, &c);
+    if (rc != LP_OK) return rc;
+    if (fast_x) *fast_x = c.fast_x;
+    if (fast_y) *fast_y = c.fast_y;
     return LP_OK;
 }

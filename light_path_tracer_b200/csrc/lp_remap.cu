@@ -16,7 +16,9 @@ lp_remap_kernel(const RemapArgs a, const CamConsts cam)
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
         const float fa32 = __ldg(a.fa32 + i);
         const unsigned wnd = a.w16 ? (unsigned)__ldg(a.w16 + i) : 0u;
-        remap_pixel<T>(a, cam, i, fa32, wnd);
+        int row, col;
+        pixel_row_col(i, a.n, cam.width, a.row0, row, col);
+        remap_pixel<T>(a, cam, i, row, col, fa32, wnd);
     }
 }
 

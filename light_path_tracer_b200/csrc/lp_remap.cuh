@@ -47,14 +47,14 @@ __device__ __forceinline__ long long pymod(long long a, long long n)
 __device__ __forceinline__ bool source_coords(const CamConsts &cam, int row, int col, float fa32,
                                               double &px, double &py)
 {
-    const double xc = cam_coord(col, cam.half_w, cam.fx);
-    const double yc = cam_coord(row, cam.half_h, cam.fy);
+    const double xc = cam_x(cam, col);
+    const double yc = cam_y(cam, row);
     const double A = fma(xc, cam.ex0, fma(yc, cam.ex1, cam.ex2));
     const double B = fma(xc, cam.ey0, fma(yc, cam.ey1, cam.ey2));
     const double n2 = fma(A, A, B * B);
     double st = 0.0, ct = 1.0;                              // arctan2(0, 0) = 0
     if (n2 > 0.0) {
-        const double inv = __ddiv_rn(1.0, __dsqrt_rn(n2));
+        const double inv = rsqrt(n2);
         st = A * inv; ct = B * inv;
     }
     double sf, cf;
@@ -78,7 +78,7 @@ __device__ __forceinline__ bool source_coords(const CamConsts &cam, int row, int
 
 template <typename T>
 __device__ __forceinline__ void remap_pixel(const RemapArgs &a, const CamConsts &cam, long long i,
-                                            float fa32, unsigned wnd)
+                                            int row, int col, float fa32, unsigned wnd)
 {
     const int C = a.channels;
     const T *__restrict__ src = (const T *)a.src;
@@ -96,8 +96,6 @@ __device__ __forceinline__ void remap_pixel(const RemapArgs &a, const CamConsts 
         }
         return;
     }
-    const int row = a.row0 + (int)(i / cam.width);
-    const int col = (int)(i % cam.width);
     double px, py;
     const bool front = source_coords(cam, row, col, fa32, px, py);
     const long long H = cam.height, W = cam.width;

@@ -65,10 +65,10 @@ lp_trace_kernel(const TraceArgs a, const BinetConsts c, const CamConsts cam)
         } else if (SRC == SRC_F32) {
             alpha = (double)__ldg((const float *)a.alphas + i);   // image_lens.py:157
         } else {
-            const int row = a.row0 + (int)(i / cam.width);
-            const int col = (int)(i % cam.width);
-            const double xc = cam_coord(col, cam.half_w, cam.fx);
-            const double yc = cam_coord(row, cam.half_h, cam.fy);
+            int row, col;
+            pixel_row_col(i, a.n, cam.width, a.row0, row, col);
+            const double xc = cam_x(cam, col);
+            const double yc = cam_y(cam, row);
             const float a32 = (float)pixel_alpha64(cam, xc, yc);     // image_lens.py:152
             if (a.out_alpha32) a.out_alpha32[i] = a32;
             alpha = (double)a32;
@@ -196,8 +196,8 @@ extern "C" int lp_schw_trace_frame(const lp_camera *h_cam, int32_t row0, int32_t
 // Same per-ray code as the kernels above followed by remap_pixel() on the float32-rounded
 // result, so the output is bit-identical to trace_frame + remap run back to back.
 // ---------------------------------------------------------------------------
-template <bool FUSED, bool FAST, typename T>
-__global__ void __launch_bounds__(LP_TRACE_BLOCK)
+template <bool FUSED, bool FAST, typename T, int MINB>
+__global__ void __launch_bounds__(LP_TRACE_BLOCK, MINB)
 lp_render_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts c, const CamConsts cam)
 {
     const LoopRegs L = load_loop_regs(c);
@@ -206,17 +206,16 @@ lp_render_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts c, con
     RayResult r;
     r.status = 0; r.steps = 0; r.nh = 0; r.fa = 0.0;
     if (live) {
-        const int row = a.row0 + (int)(i / cam.width);
-        const int col = (int)(i % cam.width);
-        const float a32 = (float)pixel_alpha64(cam, cam_coord(col, cam.half_w, cam.fx),
-                                               cam_coord(row, cam.half_h, cam.fy));
+        int row, col;
+        pixel_row_col(i, a.n, cam.width, a.row0, row, col);
+        const float a32 = (float)pixel_alpha64(cam, cam_x(cam, col), cam_y(cam, row));
         binet_trace<FUSED, FAST>(c, L, (double)a32, r);
         if (FUSED && r.steps > a.retrace_steps) binet_trace<false, FAST>(c, L, (double)a32, r);
         const float fa32 = (float)((r.status == 1) ? r.fa : __longlong_as_double(0x7ff8000000000000LL));
         const long long nh = r.nh < 0 ? 0 : (r.nh > 65535 ? 65535 : r.nh);
         if (a.out_fa) ((float *)a.out_fa)[i] = fa32;
         if (a.out_w) ((unsigned short *)a.out_w)[i] = (unsigned short)nh;
-        remap_pixel<T>(ra, cam, i, fa32, (unsigned)nh);
+        remap_pixel<T>(ra, cam, i, row, col, fa32, (unsigned)nh);
     }
     if (a.stats) {
         StatAcc acc;
@@ -226,9 +225,22 @@ lp_render_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts c, con
     }
 }
 
-template <typename T>
-static int launch_render(const TraceArgs &a, const RemapArgs &ra, const BinetConsts &c,
-                         const CamConsts &cam, uint32_t flags, cudaStream_t stream)
+// MINB = CTAs of LP_TRACE_BLOCK threads ptxas must fit per SM: 1 -> 64 registers (32 warps/SM),
+// 5 -> 48 registers (40 warps/SM, a few spills outside the loop).  LP_RENDER_MINB=5 selects the
+// second build (tuning knob).
+static int render_minb()
+{
+    static int cached = 0;
+    if (!cached) {
+        const char *e = getenv("LP_RENDER_MINB");
+        cached = (e && atoi(e) == 5) ? 5 : 1;
+    }
+    return cached;
+}
+
+template <typename T, int MINB>
+static int launch_render_mb(const TraceArgs &a, const RemapArgs &ra, const BinetConsts &c,
+                            const CamConsts &cam, uint32_t flags, cudaStream_t stream)
 {
     const bool fused = (flags & (LP_TRACE_FUSED | LP_TRACE_HYBRID)) != 0;
     const bool icmp = lp_binet_fast_ok(&c) != 0;
@@ -237,13 +249,21 @@ static int launch_render(const TraceArgs &a, const RemapArgs &ra, const BinetCon
     if (chunks > 0x7fffffffLL) return LP_ERR_UNSUPPORTED;
     const unsigned grid = (unsigned)chunks;
     if (fused) {
-        if (icmp) lp_render_kernel<true, true, T><<<grid, block, 0, stream>>>(a, ra, c, cam);
-        else      lp_render_kernel<true, false, T><<<grid, block, 0, stream>>>(a, ra, c, cam);
+        if (icmp) lp_render_kernel<true, true, T, MINB><<<grid, block, 0, stream>>>(a, ra, c, cam);
+        else      lp_render_kernel<true, false, T, MINB><<<grid, block, 0, stream>>>(a, ra, c, cam);
     } else {
-        if (icmp) lp_render_kernel<false, true, T><<<grid, block, 0, stream>>>(a, ra, c, cam);
-        else      lp_render_kernel<false, false, T><<<grid, block, 0, stream>>>(a, ra, c, cam);
+        if (icmp) lp_render_kernel<false, true, T, MINB><<<grid, block, 0, stream>>>(a, ra, c, cam);
+        else      lp_render_kernel<false, false, T, MINB><<<grid, block, 0, stream>>>(a, ra, c, cam);
     }
     return lp_check_launch();
+}
+
+template <typename T>
+static int launch_render(const TraceArgs &a, const RemapArgs &ra, const BinetConsts &c,
+                         const CamConsts &cam, uint32_t flags, cudaStream_t stream)
+{
+    if (render_minb() == 5) return launch_render_mb<T, 5>(a, ra, c, cam, flags, stream);
+    return launch_render_mb<T, 1>(a, ra, c, cam, flags, stream);
 }
 
 extern "C" int lp_render_frame(const void *src, int32_t src_dtype, int32_t channels,
@@ -289,10 +309,9 @@ lp_alpha_lookup_kernel(const CamConsts cam, int row0, long long n, int decimals,
 {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const int row = row0 + (int)(i / cam.width);
-        const int col = (int)(i % cam.width);
-        double al = pixel_alpha64(cam, cam_coord(col, cam.half_w, cam.fx),
-                                  cam_coord(row, cam.half_h, cam.fy));
+        int row, col;
+        pixel_row_col(i, n, cam.width, row0, row, col);
+        double al = pixel_alpha64(cam, cam_x(cam, col), cam_y(cam, row));
         if (decimals >= 0) al = __ddiv_rn(rint(mul_(al, scale)), scale);   // np.round(alpha, decimals)
         out[i] = (float)al;
     }

