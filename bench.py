@@ -9,8 +9,9 @@ the image_lens pipeline — per-pixel viewing angle (float32 table semantics) ->
 null-geodesic trace (fp64, the reference's own RK4 stepper; hybrid arithmetic, see `arithmetic` in config) -> deflection
 remap of a synthetic float32 RGB checkerboard — at 3840x2160, M=1, r_obs=100 M, vertical
 FOV 40 deg, psi=(0,0).  One step = one frame = ONE launch of the fused kernel
-(lp_render_frame).  N > 1: weak scaling by row tiles — the frame grows to 3840 x (2160 N),
-rank g renders its 2160-row tile and the tiles are gathered to rank 0 over NCCL.
+(lp_render_frame).  N > 1: weak scaling by row tiles — the frame grows to 3840 x (2160 N) at the
+same pixel scale, rank g renders its 2160-row tile in bands, and each finished band is gathered
+to rank 0 over NCCL while the next band is being rendered (dist.BandGather).
 
 Prints ONE JSON line on rank 0 (contract in the task statement): value = whole-job rays/s
 with the source image resident in HBM; e2e = the same through the host-buffer API with the
@@ -42,8 +43,11 @@ FLOP_PER_STEP, FLOP_PER_RAY = 43, 40     # SURVEY.md §8d work model of the inte
 
 
 def fov_for(H, W):
-    vfov = np.radians(VFOV_DEG)
-    return (2 * np.arctan(np.tan(vfov / 2) * W / H), vfov)   # image_lens.py:461-463
+    """40 deg vertical FOV for the 2160-row frame; a taller (weak-scaled) frame keeps the same
+    pixel scale, i.e. tan(vfov/2) grows with H, so every GPU's 2160-row tile holds the same
+    kind of rays as the single-GPU frame.  hfov from vfov as image_lens.py:461-463."""
+    vfov = 2 * np.arctan(np.tan(np.radians(VFOV_DEG) / 2) * H / H0)
+    return (2 * np.arctan(np.tan(vfov / 2) * W / H), vfov)
 
 
 # ---------------------------------------------------------------------------------------
@@ -153,7 +157,9 @@ def workload_config(n, H, W):
                         "-> remap), M=1, r_obs=100M, vfov=40deg, psi=(0,0), float32 RGB checkerboard source"
                         % (W, H),
             "rays_per_frame": H * W, "rows_per_gpu": H // n,
-            "parallelism": "row tiles x%d, NCCL gather to rank 0" % n if n > 1 else "single GPU",
+            "parallelism": ("row tiles x%d (2160 rows per GPU, same pixel scale as the 1-GPU frame), each tile "
+                            "rendered in bands whose NCCL gather to rank 0 overlaps the next band's render" % n)
+            if n > 1 else "single GPU",
             "arithmetic": "hybrid (LP_TRACE_HYBRID, the image pipeline's default): FMA-contracted RK4 loop, strict "
                           "re-trace of rays longer than 192 steps; same classification / winding / float32 "
                           "final_alpha as the strict kernel on this frame (tests/test_gpu_frame.py)",
@@ -207,9 +213,9 @@ def run_gpu(args):
     import lp_oracle as O                          # only for the synthetic source + CPU leg
     src_host = torch.from_numpy(O.checkerboard(H, W)).pin_memory()
     src = src_host.to("cuda", non_blocking=True)
-    tile = torch.empty((rows, W, 3), dtype=torch.float32, device="cuda")
     tile_host = torch.empty((rows, W, 3), dtype=torch.float32).pin_memory()
-    frame = torch.empty((N, rows, W, 3), dtype=torch.float32, device="cuda") if (N > 1 and rank == 0) else None
+    bg = lpdist.BandGather(rows, (W, 3), torch.float32, "cuda", dst=0, bands=args.bands) if N > 1 else None
+    tile = bg.tile if bg is not None else torch.empty((rows, W, 3), dtype=torch.float32, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def barrier():
@@ -217,13 +223,16 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def gather():
-        if N > 1:
-            dist.gather(tile, list(frame.unbind(0)) if rank == 0 else None, dst=0)
-
     def step_resident():
-        il.render_frame(src, fov, R_OBS, metric, rows=(row0, rows), out=tile)
-        gather()
+        if bg is None:
+            il.render_frame(src, fov, R_OBS, metric, rows=(row0, rows), out=tile)
+            return
+        # row tile rendered band by band; each finished band is gathered to rank 0 over NCCL
+        # while the next band is being rendered (dist.BandGather)
+        for first, n in bg.bands:
+            il.render_frame(src, fov, R_OBS, metric, rows=(row0 + first, n), out=tile[first:first + n])
+            bg.push(first, n)
+        bg.finish()
 
     def step_e2e():
         d_src = src_host.to("cuda", non_blocking=True)
@@ -325,7 +334,7 @@ def run_gpu(args):
                     "h2d_bytes_per_step": int(src_host.numel() * 4 * N),
                     "d2h_bytes_per_step": int(rays * 12),
                     "path": "pinned float32 source -> H2D -> lp_render_frame -> D2H pinned float32 frame"},
-            "gpu_launches": args.steps,
+            "gpu_launches": args.steps * (len(bg.bands) if bg is not None else 1),
             "roofline": {"bound": "fp64", "kernel": "lp_render_kernel (alpha + Binet RK4 + remap, fused)",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                          "peak_source": "measured in this run: DFMA micro-benchmark lp_bench_dfma "
@@ -377,6 +386,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--bands", type=int, default=4, help="N > 1: bands per tile for the pipelined gather")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

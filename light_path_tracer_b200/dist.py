@@ -71,6 +71,59 @@ def gather_rows(tile, height, group=None, dst=None):
     return torch.cat([buf[g, :tiles[g][1]] for g in range(world)], dim=0)
 
 
+def band_splits(rows, bands):
+    """Split a tile of `rows` rows into at most `bands` contiguous bands: [(first_row, n_rows)]."""
+    bands = max(1, min(int(bands), max(rows, 1)))
+    edges = [rows * k // bands for k in range(bands + 1)]
+    return [(edges[k], edges[k + 1] - edges[k]) for k in range(bands) if edges[k + 1] > edges[k]]
+
+
+class BandGather:
+    """Gather-to-root of equal-sized row tiles, pipelined with the render: the tile is produced
+    band by band and every finished band is handed to NCCL (async) while the next band is
+    still being rendered, so the NVLink transfer of the frame overlaps the FP64 work instead of
+    following it (at 8 GPUs the gather is the same order as the compute).
+
+        g = BandGather(rows, row_shape, dtype, device, dst=0, bands=4)
+        for first, n in g.bands:
+            render(rows=(row0 + first, n), out=g.tile[first:first + n])
+            g.push(first, n)
+        frame = g.finish()        # [world * rows, ...] on dst, None elsewhere
+
+    Works with any backend (gloo on CPU for the tests).  All ranks must own the same number of
+    rows (weak scaling, or H divisible by the world size)."""
+
+    def __init__(self, rows, row_shape, dtype, device, dst=0, bands=4, group=None):
+        import torch
+        import torch.distributed as dist
+        self.dist, self.group, self.dst = dist, group, dst
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.rows = rows
+        self.tile = torch.empty((rows,) + tuple(row_shape), dtype=dtype, device=device)
+        self.frame = (torch.empty((self.world, rows) + tuple(row_shape), dtype=dtype, device=device)
+                      if self.rank == dst else None)
+        self.bands = band_splits(rows, bands)
+        self._works = []
+
+    def push(self, first, n):
+        send = self.tile[first:first + n]
+        if self.rank == self.dst:
+            parts = [self.frame[g, first:first + n] for g in range(self.world)]
+            w = self.dist.gather(send, parts, dst=self.dst, group=self.group, async_op=True)
+        else:
+            w = self.dist.gather(send, None, dst=self.dst, group=self.group, async_op=True)
+        self._works.append(w)
+
+    def finish(self):
+        for w in self._works:
+            w.wait()
+        self._works = []
+        if self.frame is None:
+            return None
+        return self.frame.reshape((self.world * self.rows,) + tuple(self.frame.shape[2:]))
+
+
 class RowShardedRenderer:
     """Row-tile sharded lensed render (BASELINE config 4): each rank renders its tile with the
     fused kernel, then the frame is gathered over NCCL / NVLink."""
@@ -84,14 +137,38 @@ class RowShardedRenderer:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.tiles = row_tiles(self.pipe.height, self.world)
 
-    def render_tile(self, r_obs, psi=(0.0, 0.0), stats=None, flags=0, out=None):
+    def render_tile(self, r_obs, psi=(0.0, 0.0), stats=None, flags=None, out=None):
+        flags = self._default_flags() if flags is None else flags
         return self.pipe.render(r_obs, psi=psi, rows=self.tiles[self.rank], stats=stats, flags=flags, out=out)
 
-    def render(self, r_obs, psi=(0.0, 0.0), dst=None, stats=None, flags=0):
+    def render(self, r_obs, psi=(0.0, 0.0), dst=None, stats=None, flags=None):
+        flags = self._default_flags() if flags is None else flags
         tile = self.render_tile(r_obs, psi, stats, flags)
         if self.world == 1:
             return tile
         return gather_rows(tile, self.pipe.height, self.group, dst)
+
+    def render_pipelined(self, r_obs, psi=(0.0, 0.0), dst=0, bands=4, stats=None, flags=None, gather=None):
+        """Render this rank's tile band by band and gather each band while the next one is
+        being rendered (BandGather).  Needs equal tiles (H divisible by the world size).
+        Pass a BandGather to reuse its buffers across frames."""
+        flags = self._default_flags() if flags is None else flags
+        row0, rows = self.tiles[self.rank]
+        if any(r != rows for _, r in self.tiles):
+            raise ValueError("render_pipelined needs equal row tiles")
+        if gather is None:
+            gather = BandGather(rows, (self.pipe.width,) + tuple(self.pipe.src.shape[2:]), self.pipe.src.dtype,
+                                self.pipe.src.device, dst=dst, bands=bands, group=self.group)
+        for first, n in gather.bands:
+            self.pipe.render(r_obs, psi=psi, rows=(row0 + first, n), stats=stats, flags=flags,
+                             out=gather.tile[first:first + n])
+            gather.push(first, n)
+        return gather.finish()
+
+    @staticmethod
+    def _default_flags():
+        from . import _device as dev
+        return dev.TRACE_HYBRID
 
 
 def sweep_grid(n_r=32, n_psi=16, r_lo=15.0, r_hi=1000.0, psi_deg=15.0):

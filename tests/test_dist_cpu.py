@@ -20,6 +20,12 @@ def test_row_tiles_partition():
     all_frames = sorted(sum((frame_shard(512, r, 8) for r in range(8)), []))
     assert all_frames == list(range(512))
     assert len(frame_shard(512, 3, 8)) == 64
+    from light_path_tracer_b200.dist import band_splits
+    for rows in (0, 1, 5, 2160):
+        for bands in (1, 4, 7, 5000):
+            b = band_splits(rows, bands)
+            assert sum(n for _, n in b) == rows and all(n > 0 for _, n in b)
+            assert all(b[k][0] + b[k][1] == b[k + 1][0] for k in range(len(b) - 1))
     grid = sweep_grid()
     assert len(grid) == 512 and grid[0][0] == 15.0 and abs(grid[-1][0] - 1000.0) < 1e-9
 
@@ -55,6 +61,21 @@ def _worker(rank, world, port, height, q):
                 ok = ok and torch.equal(root, expect)
             else:
                 ok = ok and root is None
+        # pipelined band gather (equal tiles only): same frame, root only
+        if height % world == 0:
+            from light_path_tracer_b200.dist import BandGather
+            for bands in (1, 3, 64):
+                g = BandGather(rows, (6, 3), torch.float32, "cpu", dst=0, bands=bands)
+                for first, n in g.bands:
+                    g.tile[first:first + n] = (torch.arange(row0 + first, row0 + first + n, dtype=torch.float32)
+                                               .reshape(n, 1, 1).expand(n, 6, 3))
+                    g.push(first, n)
+                frame = g.finish()
+                if rank == 0:
+                    expect = torch.arange(height, dtype=torch.float32).reshape(height, 1, 1).expand(height, 6, 3)
+                    ok = ok and torch.equal(frame, expect)
+                else:
+                    ok = ok and frame is None
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
