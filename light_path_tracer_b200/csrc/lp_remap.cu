@@ -22,6 +22,73 @@ lp_remap_kernel(const RemapArgs a, const CamConsts cam)
     }
 }
 
+// Fast path for the common layout — float32 RGB, nearest sampling, width % 4 == 0, 16-byte
+// aligned tile pointers: one thread owns FOUR consecutive pixels of a row.  The lookups arrive
+// as one 16-byte (fa) and one 8-byte (winding) vector load per thread, the four source
+// directions are four independent fp64 chains (the latency-bound math overlaps), the twelve
+// gather loads are issued back to back before any of them is consumed, and the 48 output
+// bytes leave as three 16-byte stores, so every warp keeps ~4x more memory in flight than
+// the one-pixel-per-thread kernel (the remap is latency-, not bandwidth-limited otherwise).
+// Same per-pixel decisions as remap_pixel(), same integer source index.
+#define LP_REMAP4_BLOCK 128
+__global__ void __launch_bounds__(LP_REMAP4_BLOCK)
+lp_remap_f32rgb_x4_kernel(const RemapArgs a, const CamConsts cam)
+{
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= a.n) return;
+    int row, col;
+    pixel_row_col(i, a.n, cam.width, a.row0, row, col);
+    const float4 fa4 = __ldg(reinterpret_cast<const float4 *>(a.fa32 + i));
+    ushort4 w4 = make_ushort4(0, 0, 0, 0);
+    if (a.w16) w4 = __ldg(reinterpret_cast<const ushort4 *>(a.w16 + i));
+    const float fa[4] = {fa4.x, fa4.y, fa4.z, fa4.w};
+    const unsigned wn[4] = {w4.x, w4.y, w4.z, w4.w};
+    const float *__restrict__ src = (const float *)a.src;
+    const long long H = cam.height, W = cam.width;
+    float o[12];
+    long long off[4];
+    const double yc = cam_y(cam, row);
+    // the four source directions, unconditionally (straight-line, interleavable); pixels that
+    // do not sample the source (captured, winding) run the math on a harmless angle
+    double px[4], py[4];
+    bool front[4], samp[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        samp[p] = isfinite(fa[p]) && !(fa[p] > LP_HALF_PI_F32);
+        front[p] = source_coords_xy(cam, cam_x(cam, col + p), yc, samp[p] ? fa[p] : 0.5f, px[p], py[p]);
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        off[p] = -1;
+        const float f = fa[p];
+        if (!isfinite(f)) {
+            o[3 * p] = 0.0f; o[3 * p + 1] = 0.0f; o[3 * p + 2] = 0.0f;
+        } else if (f > LP_HALF_PI_F32) {
+            const unsigned k = wn[p] > 4u ? 4u : wn[p];
+            o[3 * p] = c_wind_rgb[k][0]; o[3 * p + 1] = c_wind_rgb[k][1]; o[3 * p + 2] = c_wind_rgb[k][2];
+        } else {
+            long long ix = (long long)rint(px[p]), iy = (long long)rint(py[p]);
+            bool ok;
+            if (a.loop_around) { ix = pymod(ix, W); iy = pymod(iy, H); ok = true; }
+            else ok = front[p] && iy >= 0 && iy < H && ix >= 0 && ix < W;
+            if (ok) off[p] = (iy * W + ix) * 3;
+            else { o[3 * p] = 1.0f; o[3 * p + 1] = 0.0f; o[3 * p + 2] = 1.0f; }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        if (off[p] >= 0) {
+            o[3 * p] = __ldg(src + off[p]);
+            o[3 * p + 1] = __ldg(src + off[p] + 1);
+            o[3 * p + 2] = __ldg(src + off[p] + 2);
+        }
+    }
+    float4 *dst = reinterpret_cast<float4 *>((float *)a.out + i * 3);
+    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+    dst[2] = make_float4(o[8], o[9], o[10], o[11]);
+}
+
 extern "C" int lp_remap(const void *src, int32_t src_dtype, int32_t channels,
                         const lp_camera *h_cam, const float *fa32, const uint16_t *w16,
                         int32_t render_loop_around, int32_t sampling,
@@ -39,6 +106,15 @@ extern "C" int lp_remap(const void *src, int32_t src_dtype, int32_t channels,
     a.row0 = row0; a.channels = channels; a.loop_around = render_loop_around; a.sampling = sampling;
     if (a.n == 0) return LP_OK;
     if (!src || !out || !fa32) return LP_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (src_dtype == LP_DTYPE_F32 && channels == 3 && sampling == LP_SAMPLE_NEAREST && cam.width % 4 == 0 &&
+        ((uintptr_t)out % 16) == 0 && ((uintptr_t)fa32 % 16) == 0 && (!w16 || ((uintptr_t)w16 % 8) == 0)) {
+        const long long quads = a.n / 4;                 // width % 4 == 0 -> n % 4 == 0
+        const long long blocks = (quads + LP_REMAP4_BLOCK - 1) / LP_REMAP4_BLOCK;
+        if (blocks > 0x7fffffffLL) return LP_ERR_UNSUPPORTED;
+        lp_remap_f32rgb_x4_kernel<<<(unsigned)blocks, LP_REMAP4_BLOCK, 0, st>>>(a, cam);
+        return lp_check_launch();
+    }
     const void *fn;
     switch (src_dtype) {
     case LP_DTYPE_U8: fn = (const void *)lp_remap_kernel<unsigned char>; break;
@@ -51,7 +127,6 @@ extern "C" int lp_remap(const void *src, int32_t src_dtype, int32_t channels,
     if (rc != LP_OK) return rc;
     const long long chunks = (a.n + 255) / 256;
     if (chunks < grid) grid = (int)chunks;
-    cudaStream_t st = (cudaStream_t)stream;
     switch (src_dtype) {
     case LP_DTYPE_U8: lp_remap_kernel<unsigned char><<<grid, 256, 0, st>>>(a, cam); break;
     case LP_DTYPE_F32: lp_remap_kernel<float><<<grid, 256, 0, st>>>(a, cam); break;

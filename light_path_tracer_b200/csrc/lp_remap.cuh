@@ -34,6 +34,65 @@ __device__ __forceinline__ long long pymod(long long a, long long n)
     return m < 0 ? m + n : m;
 }
 
+// ---------------------------------------------------------------------------
+// Branch-free fp64 helpers for the remap.  What has to match the reference there is the
+// INTEGER source index rint(px), rint(py) (image_lens.py:367-375): the continuous coordinate
+// only needs ~1e-12 relative accuracy (a tie would have to be that close to a half-integer to
+// flip), so these trade the library routines' last-ulp guarantees and special-case branches
+// (which keep ptxas from interleaving neighbouring pixels' dependency chains) for straight-line
+// code accurate to a few ulp.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double fast_rcp(double x)        // x finite, normal, != 0
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));   // MUFU.RCP64H, ~20 bits
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+
+__device__ __forceinline__ double fast_rsqrt(double x)      // x finite, normal, > 0
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x)); // MUFU.RSQ64H, ~20 bits
+    const double hx = 0.5 * x;
+    y = fma(y, fma(-hx * y, y, 0.5), y);
+    y = fma(y, fma(-hx * y, y, 0.5), y);
+    return y;
+}
+
+// fdlibm kernel polynomials (k_sin.c / k_cos.c), |r| <= pi/4, < 1 ulp
+static __constant__ double c_sin_poly[6] = {-1.66666666666666324348e-01, 8.33333333332248946124e-03,
+                                            -1.98412698298579493134e-04, 2.75573137070700676789e-06,
+                                            -2.50507602534068634195e-08, 1.58969099521155010221e-10};
+static __constant__ double c_cos_poly[6] = {4.16666666666666019037e-02, -1.38888888888741095749e-03,
+                                            2.48015872894767294178e-05, -2.75573143513906633035e-07,
+                                            2.08757232129817482790e-09, -1.13596475577881948265e-11};
+
+// sin and cos of a moderate argument (|x| up to a few pi; the remap passes final_alpha in
+// [0, pi/2]): two-term Cody-Waite reduction by pi/2, the two kernel polynomials, quadrant select.
+__device__ __forceinline__ void sincos_moderate(double x, double &s, double &c)
+{
+    const double shifter = 6755399441055744.0;               // 1.5 * 2^52
+    const double qf = fma(x, 0.63661977236758138, shifter);  // x * 2/pi, rounded to nearest integer
+    const int q = __double2loint(qf);
+    const double n = qf - shifter;
+    double r = fma(-n, 1.5707963267948966, x);               // pi/2 hi
+    r = fma(-n, 6.123233995736766e-17, r);                   // pi/2 lo
+    const double z = r * r;
+    double ps = c_sin_poly[5];
+    double pc = c_cos_poly[5];
+#pragma unroll
+    for (int k = 4; k >= 0; --k) { ps = fma(ps, z, c_sin_poly[k]); pc = fma(pc, z, c_cos_poly[k]); }
+    const double sr = fma(r * z, ps, r);
+    const double cr = fma(z * z, pc, fma(-0.5, z, 1.0));
+    const double s0 = (q & 1) ? cr : sr;
+    const double c0 = (q & 1) ? sr : cr;
+    s = (q & 2) ? -s0 : s0;
+    c = ((q + 1) & 2) ? -c0 : c0;
+}
+
 // Source direction of an escaped pixel -> pinhole plane coordinates (image_lens.py:310-352).
 // Returns front (src_vz > 1e-12) and the continuous source pixel coordinates.
 //
@@ -41,24 +100,18 @@ __device__ __forceinline__ long long pymod(long long a, long long n)
 // sin(theta), cos(theta).  theta is invariant under scaling of v, and sin/cos of an arctan2
 // are the normalised components themselves, so here (st, ct) = (A, B)/hypot(A, B) with
 // A, B the dot products of the UN-normalised ray (x_cam, y_cam, 1): no arctan2, no second
-// sincos, no normalisation of v.  What has to match the reference is the INTEGER source
-// index rint(px), rint(py); the two evaluations differ by a few ulp of px (~1e-13 pixel), so
-// they can only disagree on a tie that is that close to a half-integer.
-__device__ __forceinline__ bool source_coords(const CamConsts &cam, int row, int col, float fa32,
-                                              double &px, double &py)
+// sincos, no normalisation of v.  Straight-line code (see the helpers above).
+__device__ __forceinline__ bool source_coords_xy(const CamConsts &cam, double xc, double yc, float fa32,
+                                                 double &px, double &py)
 {
-    const double xc = cam_x(cam, col);
-    const double yc = cam_y(cam, row);
     const double A = fma(xc, cam.ex0, fma(yc, cam.ex1, cam.ex2));
     const double B = fma(xc, cam.ey0, fma(yc, cam.ey1, cam.ey2));
     const double n2 = fma(A, A, B * B);
-    double st = 0.0, ct = 1.0;                              // arctan2(0, 0) = 0
-    if (n2 > 0.0) {
-        const double inv = rsqrt(n2);
-        st = A * inv; ct = B * inv;
-    }
+    const bool on_axis = !(n2 > 1e-300);                    // arctan2(0, 0) = 0
+    const double inv = fast_rsqrt(on_axis ? 1.0 : n2);
+    const double st = on_axis ? 0.0 : A * inv, ct = on_axis ? 1.0 : B * inv;
     double sf, cf;
-    sincos((double)fa32, &sf, &cf);                         // image_lens.py:340-346
+    sincos_moderate((double)fa32, sf, cf);                  // image_lens.py:340-346
     const double tx = fma(st, cam.ex0, ct * cam.ey0);
     const double ty = fma(st, cam.ex1, ct * cam.ey1);
     const double tz = fma(st, cam.ex2, ct * cam.ey2);
@@ -66,14 +119,17 @@ __device__ __forceinline__ bool source_coords(const CamConsts &cam, int row, int
     const double sy = fma(cf, cam.d1, sf * ty);
     const double sz = fma(cf, cam.d2, sf * tz);
     const bool front = sz > 1e-12;
-    if (front) {
-        px = fma(__ddiv_rn(sx, sz), cam.fx, cam.half_w);          // image_lens.py:374
-        py = fma(__ddiv_rn(sy, sz), cam.fy, cam.half_h);
-    } else {
-        px = cam.half_w;                                          // image_lens.py:356-361 (zeros * f + n/2)
-        py = cam.half_h;
-    }
+    const double isz = fast_rcp(front ? sz : 1.0);
+    // behind the camera: zeros * f + n/2 (image_lens.py:356-361)
+    px = front ? fma(sx * isz, cam.fx, cam.half_w) : cam.half_w;    // image_lens.py:374
+    py = front ? fma(sy * isz, cam.fy, cam.half_h) : cam.half_h;
     return front;
+}
+
+__device__ __forceinline__ bool source_coords(const CamConsts &cam, int row, int col, float fa32,
+                                              double &px, double &py)
+{
+    return source_coords_xy(cam, cam_x(cam, col), cam_y(cam, row), fa32, px, py);
 }
 
 template <typename T>

@@ -225,7 +225,7 @@ lp_render_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts c, con
     }
 }
 
-// MINB = CTAs of LP_TRACE_BLOCK threads ptxas must fit per SM: 1 -> 64 registers (32 warps/SM),
+// MINB = CTAs of LP_TRACE_BLOCK threads ptxas must fit per SM: 4 -> 64 registers (32 warps/SM),
 // 5 -> 48 registers (40 warps/SM, a few spills outside the loop).  LP_RENDER_MINB=5 selects the
 // second build (tuning knob).
 static int render_minb()
@@ -233,7 +233,7 @@ static int render_minb()
     static int cached = 0;
     if (!cached) {
         const char *e = getenv("LP_RENDER_MINB");
-        cached = (e && atoi(e) == 5) ? 5 : 1;
+        cached = (e && atoi(e) == 5) ? 5 : 4;
     }
     return cached;
 }
@@ -263,7 +263,7 @@ static int launch_render(const TraceArgs &a, const RemapArgs &ra, const BinetCon
                          const CamConsts &cam, uint32_t flags, cudaStream_t stream)
 {
     if (render_minb() == 5) return launch_render_mb<T, 5>(a, ra, c, cam, flags, stream);
-    return launch_render_mb<T, 1>(a, ra, c, cam, flags, stream);
+    return launch_render_mb<T, 4>(a, ra, c, cam, flags, stream);
 }
 
 extern "C" int lp_render_frame(const void *src, int32_t src_dtype, int32_t channels,
