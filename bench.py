@@ -144,7 +144,7 @@ def run_reference(args):
         "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.gpus, H, W),
+        "config": workload_config(args.gpus, H, W, args.gather if args.gpus > 1 else "none"),
         "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -152,13 +152,16 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n, H, W):
+def workload_config(n, H, W, gather_mode="nccl"):
     return {"workload": "image_lens Schwarzschild lensed render %dx%d (alpha lookup -> Binet RK4 trace "
                         "-> remap), M=1, r_obs=100M, vfov=40deg, psi=(0,0), float32 RGB checkerboard source"
                         % (W, H),
             "rays_per_frame": H * W, "rows_per_gpu": H // n,
-            "parallelism": ("row tiles x%d (2160 rows per GPU, same pixel scale as the 1-GPU frame), each tile "
-                            "rendered in bands whose NCCL gather to rank 0 overlaps the next band's render" % n)
+            "parallelism": ("row tiles x%d (2160 rows per GPU, same pixel scale as the 1-GPU frame); " % n +
+                            ("every rank's render kernel stores its tile straight into rank 0's frame through "
+                             "NVLink peer memory (symmetric memory), one 4-byte NCCL all-reduce orders completion"
+                             if gather_mode == "peer" else
+                             "each tile rendered in bands whose NCCL gather to rank 0 overlaps the next band's render"))
             if n > 1 else "single GPU",
             "arithmetic": "hybrid (LP_TRACE_HYBRID, the image pipeline's default): FMA-contracted RK4 loop, strict "
                           "re-trace of rays longer than 192 steps; same classification / winding / float32 "
@@ -214,8 +217,29 @@ def run_gpu(args):
     src_host = torch.from_numpy(O.checkerboard(H, W)).pin_memory()
     src = src_host.to("cuda", non_blocking=True)
     tile_host = torch.empty((rows, W, 3), dtype=torch.float32).pin_memory()
-    bg = lpdist.BandGather(rows, (W, 3), torch.float32, "cuda", dst=0, bands=args.bands) if N > 1 else None
-    tile = bg.tile if bg is not None else torch.empty((rows, W, 3), dtype=torch.float32, device="cuda")
+    # N > 1: where the tile goes.  "peer": straight into rank 0's frame through NVLink peer memory
+    # (the render kernel's own stores; dist.PeerFrame).  "nccl": local tile, then NCCL gather of
+    # row bands overlapped with the next band's render (dist.BandGather).
+    bg = pf = None
+    gather_mode = "none"
+    if N > 1:
+        gather_mode = args.gather
+        if gather_mode == "peer":
+            try:
+                pf = lpdist.PeerFrame(H, (W, 3), torch.float32, torch.device("cuda", local), dst=0)
+            except Exception as exc:      # symmetric memory unavailable: say so and use NCCL
+                sys.stderr.write("PeerFrame unavailable (%r): falling back to the NCCL band gather\n" % (exc,))
+                gather_mode = "nccl"
+        # every rank must take the same path
+        agree = torch.tensor([1.0 if gather_mode == "peer" else 0.0], device="cuda")
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+        if gather_mode == "peer" and float(agree[0]) == 0.0:
+            gather_mode, pf = "nccl", None
+        if gather_mode == "nccl":
+            bg = lpdist.BandGather(rows, (W, 3), torch.float32, "cuda", dst=0, bands=args.bands)
+    tile = pf.tile if pf is not None else (bg.tile if bg is not None else
+                                           torch.empty((rows, W, 3), dtype=torch.float32, device="cuda"))
+    local_tile = torch.empty((rows, W, 3), dtype=torch.float32, device="cuda") if pf is not None else tile
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def barrier():
@@ -224,6 +248,11 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     def step_resident():
+        if pf is not None:
+            il.render_frame(src, fov, R_OBS, metric, rows=(row0, rows), out=tile,
+                            flags=dev.TRACE_HYBRID | dev.RENDER_STAGED_STORES)
+            pf.complete()
+            return
         if bg is None:
             il.render_frame(src, fov, R_OBS, metric, rows=(row0, rows), out=tile)
             return
@@ -236,8 +265,8 @@ def run_gpu(args):
 
     def step_e2e():
         d_src = src_host.to("cuda", non_blocking=True)
-        il.render_frame(d_src, fov, R_OBS, metric, rows=(row0, rows), out=tile)
-        tile_host.copy_(tile, non_blocking=True)
+        il.render_frame(d_src, fov, R_OBS, metric, rows=(row0, rows), out=local_tile)
+        tile_host.copy_(local_tile, non_blocking=True)
 
     def timed(step, k):
         """k steps, each bracketed by CUDA events on the launching stream; L2 flushed in between.
@@ -272,7 +301,7 @@ def run_gpu(args):
 
     # dominant kernel alone (no gather), same events: roofline numerator / denominator
     def step_kernel():
-        il.render_frame(src, fov, R_OBS, metric, rows=(row0, rows), out=tile)
+        il.render_frame(src, fov, R_OBS, metric, rows=(row0, rows), out=local_tile)
     ms_k = timed(step_kernel, args.steps)
     kern_ms = float(np.mean(ms_k))
 
@@ -328,13 +357,14 @@ def run_gpu(args):
             "value": value, "unit": "rays/s", "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(N, H, W),
+            "config": workload_config(N, H, W, gather_mode),
             "ms_per_frame": total_ms / args.steps,
             "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_frame": total_e2e / args.steps,
                     "h2d_bytes_per_step": int(src_host.numel() * 4 * N),
                     "d2h_bytes_per_step": int(rays * 12),
                     "path": "pinned float32 source -> H2D -> lp_render_frame -> D2H pinned float32 frame"},
             "gpu_launches": args.steps * (len(bg.bands) if bg is not None else 1),
+            "gather": gather_mode,
             "roofline": {"bound": "fp64", "kernel": "lp_render_kernel (alpha + Binet RK4 + remap, fused)",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                          "peak_source": "measured in this run: DFMA micro-benchmark lp_bench_dfma "
@@ -386,7 +416,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--bands", type=int, default=4, help="N > 1: bands per tile for the pipelined gather")
+    ap.add_argument("--bands", type=int, default=4, help="N > 1, --gather nccl: bands per tile")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: peer = tiles stored straight into rank 0's frame over NVLink peer memory; "
+                         "nccl = NCCL gather of row bands overlapped with the render")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -53,6 +53,11 @@ extern "C" {
                                      amplified): same classification and winding as
                                      LP_TRACE_STRICT, final_alpha within 1e-9 relative  */
 
+#define LP_RENDER_STAGED_STORES 8u /* lp_render_frame, float32 RGB: stage each warp's 32 pixels in
+                                     shared memory and store them as 16-byte vectors (full
+                                     sectors).  For tiles that live in a PEER GPU's memory
+                                     (NVLink): ~1 % slower than plain stores into local HBM  */
+
 /* ---- ray status codes (metrics.py:69, :125) ------------------------------ */
 #define LP_RAY_ESCAPED    1
 #define LP_RAY_CAPTURED (-1)

@@ -18,7 +18,7 @@ lp_remap_kernel(const RemapArgs a, const CamConsts cam)
         const unsigned wnd = a.w16 ? (unsigned)__ldg(a.w16 + i) : 0u;
         int row, col;
         pixel_row_col(i, a.n, cam.width, a.row0, row, col);
-        remap_pixel<T>(a, cam, i, row, col, fa32, wnd);
+        remap_pixel<T>(a, cam, (T *)a.out + i * a.channels, row, col, fa32, wnd);
     }
 }
 
@@ -104,6 +104,7 @@ extern "C" int lp_remap(const void *src, int32_t src_dtype, int32_t channels,
     a.src = src; a.out = out; a.fa32 = fa32; a.w16 = w16;
     a.n = (long long)rows * cam.width;
     a.row0 = row0; a.channels = channels; a.loop_around = render_loop_around; a.sampling = sampling;
+    a.vec_ok = 0;
     if (a.n == 0) return LP_OK;
     if (!src || !out || !fa32) return LP_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;

@@ -25,6 +25,7 @@ struct RemapArgs {
     int32_t channels;
     int32_t loop_around;
     int32_t sampling;
+    int32_t vec_ok;              // fused kernel: float32 RGB into a 16-byte aligned tile
 };
 
 // python `a % n` for n > 0
@@ -42,26 +43,6 @@ __device__ __forceinline__ long long pymod(long long a, long long n)
 // (which keep ptxas from interleaving neighbouring pixels' dependency chains) for straight-line
 // code accurate to a few ulp.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ double fast_rcp(double x)        // x finite, normal, != 0
-{
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));   // MUFU.RCP64H, ~20 bits
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    return fma(r, e, r);
-}
-
-__device__ __forceinline__ double fast_rsqrt(double x)      // x finite, normal, > 0
-{
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x)); // MUFU.RSQ64H, ~20 bits
-    const double hx = 0.5 * x;
-    y = fma(y, fma(-hx * y, y, 0.5), y);
-    y = fma(y, fma(-hx * y, y, 0.5), y);
-    return y;
-}
-
 // fdlibm kernel polynomials (k_sin.c / k_cos.c), |r| <= pi/4, < 1 ulp
 static __constant__ double c_sin_poly[6] = {-1.66666666666666324348e-01, 8.33333333332248946124e-03,
                                             -1.98412698298579493134e-04, 2.75573137070700676789e-06,
@@ -133,12 +114,11 @@ __device__ __forceinline__ bool source_coords(const CamConsts &cam, int row, int
 }
 
 template <typename T>
-__device__ __forceinline__ void remap_pixel(const RemapArgs &a, const CamConsts &cam, long long i,
+__device__ __forceinline__ void remap_pixel(const RemapArgs &a, const CamConsts &cam, T *__restrict__ dst,
                                             int row, int col, float fa32, unsigned wnd)
-{
+{   // dst: where this pixel's `channels` values go (global memory, or a staging slot)
     const int C = a.channels;
     const T *__restrict__ src = (const T *)a.src;
-    T *__restrict__ dst = (T *)a.out + i * C;
     if (!isfinite(fa32)) {                                   // captured / invalid: zeros_like
         for (int ch = 0; ch < C; ++ch) dst[ch] = (T)0;
         return;

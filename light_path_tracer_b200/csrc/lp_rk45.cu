@@ -31,9 +31,11 @@
 // are build specific, so bit equality with scipy is not attainable by any order (SURVEY.md
 // 7.3 H7); measured agreement with the reference: see tests/test_gpu_rk45.py.
 #include "lp_internal.cuh"
+#include <stdlib.h>
 
 #define RK_BLOCK 128
 #define RK_REFILL_MIN 4
+#define RK_DEFAULT_MINB 2
 #define RK_NC 6            /* moving components: t, r, theta, phi, p_r, p_theta */
 
 static __constant__ double c_A[6][5] = {
@@ -86,18 +88,42 @@ __device__ __forceinline__ void rk_rhs(double R_S, double r_floor, double p_t, d
         return;
     }
     if (th != tc.th) { sincos(th, &tc.s, &tc.c); tc.th = th; }
-    const double f = 1.0 - R_S / r;
     double s2 = tc.s * tc.s;
     if (s2 < 1e-15) s2 = 1e-15;
+    const double pp2 = p_phi * p_phi;
+#ifdef LP_RK45_EXACT_DIV
+    // the reference's expression tree, one IEEE division per `/` (9 per evaluation)
+    const double f = 1.0 - R_S / r;
     const double r2 = r * r, r3 = r * r * r;
     const double a = R_S / (2.0 * r2);
-    const double pp2 = p_phi * p_phi;
     d[0] = -p_t / f;
     d[1] = f * p_r;
     d[2] = p_th / r2;
     d[3] = p_phi / (r2 * s2);
     d[4] = (-a * ((p_t * p_t) / (f * f)) - a * (p_r * p_r)) + ((p_th * p_th) + pp2 / s2) / r3;
     d[5] = tc.c * pp2 / (r2 * s2 * tc.s);
+#else
+    // Same expressions with the nine divisions replaced by products of three reciprocals
+    // (1/r, 1/f and, off the equator only, 1/sin theta): every term within a few ulp of the
+    // reference's.  That is the level at which scipy's own BLAS stage sums already differ from
+    // any restatement, and it removes most of the FP64-pipe work of an evaluation (an IEEE
+    // division is ~12 dependent pipe slots); tests/test_gpu_rk45.py holds the result to the same
+    // bar (identical accept/reject sequences, final state <= 1e-9).
+    const double ir = fast_rcp(r);
+    const double ir2 = ir * ir, ir3 = ir2 * ir;
+    const double f = 1.0 - R_S * ir;
+    const double inv_f = fast_rcp(f);
+    double is2 = 1.0, is1 = tc.s;                          // equatorial plane: sin(theta) = +-1 exactly
+    if (s2 != 1.0) { is2 = fast_rcp(s2); is1 = fast_rcp(tc.s); }
+    const double a = 0.5 * R_S * ir2;
+    const double ptf = p_t * inv_f;
+    d[0] = -ptf;
+    d[1] = f * p_r;
+    d[2] = p_th * ir2;
+    d[3] = p_phi * ir2 * is2;
+    d[4] = (-a * (ptf * ptf) - a * (p_r * p_r)) + ((p_th * p_th) + pp2 * is2) * ir3;
+    d[5] = tc.c * pp2 * ir2 * is2 * is1;
+#endif
 }
 
 // Quartic dense output of one component (rk.py:723-737), sequential like the oracle.
@@ -169,7 +195,8 @@ __device__ __forceinline__ void write_point(const Rk45Args &a, long long idx, in
     row[5] = p_t; row[6] = y[4]; row[7] = y[5]; row[8] = p_phi;
 }
 
-__global__ void __launch_bounds__(RK_BLOCK)
+template <int MINB>
+__global__ void __launch_bounds__(RK_BLOCK, MINB)
 lp_rk45_kernel(const Rk45Args a)
 {
     const unsigned full = 0xffffffffu;
@@ -446,12 +473,24 @@ static int rk45_launch(const double *alphas, const double *state0, int64_t n, do
     a.out_state = out_state; a.out_lambda = out_lambda; a.out_outcome = out_outcome;
     a.out_nsteps = out_nsteps; a.out_status = out_status;
     a.traj = traj; a.max_points = max_points; a.n_points = n_points;
+    // resident CTAs per SM ptxas must fit: 2 -> 202 registers, no spills; 3 -> 168; 4 -> 128 (spills).
+    // LP_RK45_MINB selects (tuning knob); the default is the measured best.
+    static int minb = 0;
+    if (!minb) {
+        const char *e = getenv("LP_RK45_MINB");
+        const int v = e ? atoi(e) : 0;
+        minb = (v == 2 || v == 3 || v == 4) ? v : RK_DEFAULT_MINB;
+    }
+    const void *fn = minb == 2 ? (const void *)lp_rk45_kernel<2>
+                   : minb == 3 ? (const void *)lp_rk45_kernel<3> : (const void *)lp_rk45_kernel<4>;
     int grid = 0;
-    int rc = lp_grid_for((const void *)lp_rk45_kernel, RK_BLOCK, &grid);
+    int rc = lp_grid_for(fn, RK_BLOCK, &grid);
     if (rc != LP_OK) return rc;
     const long long chunks = (n + RK_BLOCK - 1) / RK_BLOCK;
     if (chunks < grid) grid = (int)chunks;
-    lp_rk45_kernel<<<grid, RK_BLOCK, 0, stream>>>(a);
+    if (minb == 2) lp_rk45_kernel<2><<<grid, RK_BLOCK, 0, stream>>>(a);
+    else if (minb == 3) lp_rk45_kernel<3><<<grid, RK_BLOCK, 0, stream>>>(a);
+    else lp_rk45_kernel<4><<<grid, RK_BLOCK, 0, stream>>>(a);
     return lp_check_launch();
 }
 

@@ -203,6 +203,13 @@ lp_render_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts c, con
     const LoopRegs L = load_loop_regs(c);
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < a.n;
+    // float32 RGB into a 16-byte aligned tile: a full warp's 32 pixels (384 contiguous bytes)
+    // are staged in shared memory and leave as 24 16-byte stores instead of 96 4-byte ones —
+    // full sectors, which is what peer (NVLink) destinations need (dist.PeerFrame).
+    __shared__ __align__(16) float stage[LP_TRACE_BLOCK / 32][96];
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const long long i0 = i - lane;
+    const bool vec = sizeof(T) == 4 && ra.vec_ok && (i0 + 31 < a.n);      // warp-uniform
     RayResult r;
     r.status = 0; r.steps = 0; r.nh = 0; r.fa = 0.0;
     if (live) {
@@ -215,7 +222,13 @@ lp_render_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts c, con
         const long long nh = r.nh < 0 ? 0 : (r.nh > 65535 ? 65535 : r.nh);
         if (a.out_fa) ((float *)a.out_fa)[i] = fa32;
         if (a.out_w) ((unsigned short *)a.out_w)[i] = (unsigned short)nh;
-        remap_pixel<T>(ra, cam, i, row, col, fa32, (unsigned)nh);
+        T *dst = vec ? (T *)&stage[wrp][lane * 3] : (T *)ra.out + i * ra.channels;
+        remap_pixel<T>(ra, cam, dst, row, col, fa32, (unsigned)nh);
+    }
+    if (vec) {
+        __syncwarp();
+        if (lane < 24)
+            reinterpret_cast<float4 *>((float *)ra.out + i0 * 3)[lane] = reinterpret_cast<const float4 *>(stage[wrp])[lane];
     }
     if (a.stats) {
         StatAcc acc;
@@ -291,6 +304,8 @@ extern "C" int lp_render_frame(const void *src, int32_t src_dtype, int32_t chann
     RemapArgs ra;
     ra.src = src; ra.out = out; ra.fa32 = nullptr; ra.w16 = nullptr; ra.n = n;
     ra.row0 = row0; ra.channels = channels; ra.loop_around = render_loop_around; ra.sampling = sampling;
+    ra.vec_ok = ((flags & LP_RENDER_STAGED_STORES) && src_dtype == LP_DTYPE_F32 && channels == 3 &&
+                 ((uintptr_t)out % 16) == 0) ? 1 : 0;
     cudaStream_t st = (cudaStream_t)stream;
     switch (src_dtype) {
     case LP_DTYPE_U8: return launch_render<unsigned char>(a, ra, c, cam, flags, st);

@@ -124,6 +124,43 @@ class BandGather:
         return self.frame.reshape((self.world * self.rows,) + tuple(self.frame.shape[2:]))
 
 
+class PeerFrame:
+    """The frame lives in rank `dst`'s HBM and every rank's render kernel stores its row tile
+    STRAIGHT INTO IT through NVLink peer memory (torch symmetric memory: CUDA VMM allocations
+    mapped into every process of the group).  The "gather" is the kernel's own pixel stores —
+    16-byte vectors, see lp_render_kernel — so the transfer overlaps the FP64 work store by
+    store and there is no copy kernel and no data-path collective; one tiny all-reduce orders
+    "every rank's kernel has finished" before rank `dst` reads the frame.
+
+        pf = PeerFrame(H, (W, 3), torch.float32, device)       # collective (rendezvous)
+        render(rows=pf.rows, out=pf.tile)                      # every rank, its own tile
+        frame = pf.complete()                                  # [H, W, 3] on dst, None elsewhere
+
+    Raises if symmetric memory is unavailable (callers fall back to BandGather / gather_rows)."""
+
+    def __init__(self, height, row_shape, dtype, device, dst=0, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.dist, self.dst = dist, dst
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        shape = (height,) + tuple(row_shape)
+        self.buf = symm_mem.empty(shape, dtype=dtype, device=device)
+        self.handle = symm_mem.rendezvous(self.buf, self.group)
+        self.root = self.handle.get_buffer(dst, shape, dtype)
+        self.rows = row_tiles(height, self.world)[self.rank]
+        self.tile = self.root[self.rows[0]:self.rows[0] + self.rows[1]]
+        self._flag = torch.zeros(1, dtype=torch.float32, device=device)
+
+    def complete(self):
+        # stream-ordered after this rank's render kernel; finishes on dst only after every
+        # rank's kernel (and therefore its peer stores) has finished
+        self.dist.all_reduce(self._flag, group=self.group)
+        return self.buf if self.rank == self.dst else None
+
+
 class RowShardedRenderer:
     """Row-tile sharded lensed render (BASELINE config 4): each rank renders its tile with the
     fused kernel, then the frame is gathered over NCCL / NVLink."""
@@ -164,6 +201,17 @@ class RowShardedRenderer:
                              out=gather.tile[first:first + n])
             gather.push(first, n)
         return gather.finish()
+
+    def render_peer(self, r_obs, psi=(0.0, 0.0), stats=None, flags=None, frame=None, dst=0):
+        """Render this rank's tile directly into rank dst's frame over NVLink (PeerFrame)."""
+        flags = self._default_flags() if flags is None else flags
+        if frame is None:
+            frame = PeerFrame(self.pipe.height, (self.pipe.width,) + tuple(self.pipe.src.shape[2:]),
+                              self.pipe.src.dtype, self.pipe.src.device, dst=dst, group=self.group)
+        from . import _device as dev
+        self.pipe.render(r_obs, psi=psi, rows=frame.rows, stats=stats, flags=flags | dev.RENDER_STAGED_STORES,
+                         out=frame.tile)
+        return frame.complete()
 
     @staticmethod
     def _default_flags():

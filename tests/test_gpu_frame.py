@@ -263,3 +263,29 @@ def test_frame_1080p_vs_oracle(native, oracle):
     fused = il.render_frame(torch.from_numpy(src).cuda(), fov, 100.0, metric).cpu().numpy()
     bad = (np.abs(np.floor(fused * 255) - np.floor(ref * 255)) > 1).any(-1)
     assert bad.sum() <= 4, "%d pixels differ by more than 1/255" % int(bad.sum())
+
+
+def test_staged_stores_same_frame(native):
+    """LP_RENDER_STAGED_STORES (16-byte pixel stores through shared memory, used for peer-memory
+    tiles) writes exactly the frame the plain stores write — full frame, a row tile whose pixel
+    count is not a multiple of 32, and a misaligned tile (falls back to plain stores)."""
+    import torch
+    from light_path_tracer_b200 import _device as dev
+    il = _il()
+    metric = _metric(1.0)
+    for H, W in ((270, 480), (101, 250)):
+        vfov = np.radians(40.0)
+        fov = (2 * np.arctan(np.tan(vfov / 2) * W / H), vfov)
+        src = torch.rand(H, W, 3, device="cuda")
+        ref = il.render_frame(src, fov, 100.0, metric)
+        out = il.render_frame(src, fov, 100.0, metric, flags=dev.TRACE_HYBRID | dev.RENDER_STAGED_STORES)
+        assert torch.equal(ref, out)
+        big = torch.full((H * W * 3 + 8,), -1.0, device="cuda")
+        for shift, rows in ((0, (7, H - 20)), (1, (0, H)), (4, (3, 50))):
+            n = rows[1] * W * 3
+            view = big[shift:shift + n].view(rows[1], W, 3)
+            big.fill_(-1.0)
+            il.render_frame(src, fov, 100.0, metric, rows=rows, out=view,
+                            flags=dev.TRACE_HYBRID | dev.RENDER_STAGED_STORES)
+            assert torch.equal(view, ref[rows[0]:rows[0] + rows[1]])
+            assert (big[:shift] == -1).all() and (big[shift + n:] == -1).all()

@@ -1,0 +1,71 @@
+"""Multi-GPU data path on real devices (needs >= 2 GPUs; skipped otherwise): a frame rendered
+as row tiles by two ranks — NCCL band gather and NVLink peer-memory stores — must be
+bit-identical to the single-GPU frame (SURVEY.md §8e correctness test)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from light_path_tracer_b200 import dist as lpdist, image_lens as il
+    from light_path_tracer_b200.metrics import Schwarzschild
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        H, W = 540, 960
+        g = torch.Generator().manual_seed(3)
+        src = torch.rand(H, W, 3, generator=g).cuda()
+        metric = Schwarzschild(1.0)
+        rs = lpdist.RowShardedRenderer(src, 40.0, metric)
+        full = il.render_frame(src, rs.pipe.fov, 30.0, metric, psi=(0.05, -0.02))
+        res = {}
+        a = rs.render(30.0, psi=(0.05, -0.02), dst=0)
+        b = rs.render_pipelined(30.0, psi=(0.05, -0.02), dst=0, bands=3)
+        try:
+            c = rs.render_peer(30.0, psi=(0.05, -0.02), dst=0)
+            peer_ok = True
+        except Exception as exc:                      # symmetric memory not available on this box
+            c, peer_ok = None, repr(exc)
+        if rank == 0:
+            res = {"gather": bool(torch.equal(a, full)), "bands": bool(torch.equal(b, full)),
+                   "peer": (bool(torch.equal(c, full)) if peer_ok is True else peer_ok)}
+        every = rs.render(30.0, psi=(0.05, -0.02), dst=None)      # all_gather: every rank gets the frame
+        res["all"] = bool(torch.equal(every, full))
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_frame_bit_identical(native):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert results[0]["gather"] and results[0]["bands"] and results[0]["all"] and results[1]["all"]
+    assert results[0]["peer"] is True, results[0]["peer"]
