@@ -102,9 +102,25 @@ def test_batch_vs_oracle(native, oracle, M, r_obs):
     err = (np.abs(state - s_o) / np.maximum(np.abs(s_o), FLOOR)).max(axis=1)
     err_l = np.abs(lam - l_o) / np.maximum(np.abs(l_o), 1.0)
     ok = valid & same_steps
-    print("M=%g r_obs=%g: %d rays, %d with a different accept/reject sequence; worst rel err %.2e (state) %.2e (lambda)"
-          % (M, r_obs, alpha.size, int((valid & ~same_steps).sum()), err[ok].max(), err_l[ok].max()))
-    assert err[ok].max() <= REL_TOL and err_l[ok].max() <= REL_TOL
+    # Conditioning clause: a ray that grazes the photon sphere amplifies ANY rounding
+    # difference (the kernel's reciprocals and fma sums, scipy's BLAS sums) like 1/|b - b_crit|.
+    # Measure that amplification with the oracle itself — how far does the reference's own
+    # result move when the viewing angle moves by ONE ulp — and allow twice that on top of 1e-9.
+    # It is below 1e-12 for all but a handful of rays per batch.
+    spread = np.zeros(alpha.size)
+    spread_l = np.zeros(alpha.size)
+    for shifted in (np.nextafter(alpha, np.inf), np.nextafter(alpha, -np.inf)):
+        s_p, l_p, _, _, _ = oracle.rk45_trace_batch(M, r_obs, shifted)
+        with np.errstate(invalid="ignore"):
+            spread = np.fmax(spread, (np.abs(s_p - s_o) / np.maximum(np.abs(s_o), FLOOR)).max(axis=1))
+            spread_l = np.fmax(spread_l, np.abs(l_p - l_o) / np.maximum(np.abs(l_o), 1.0))
+    tol, tol_l = REL_TOL + 2 * spread, REL_TOL + 2 * spread_l
+    print("M=%g r_obs=%g: %d rays, %d with a different accept/reject sequence; worst rel err %.2e (state) "
+          "%.2e (lambda); %d rays with 1-ulp sensitivity above 1e-10 (max %.2e)"
+          % (M, r_obs, alpha.size, int((valid & ~same_steps).sum()), err[ok].max(), err_l[ok].max(),
+             int((spread > 1e-10).sum()), spread.max()))
+    assert (err[ok] <= tol[ok]).all() and (err_l[ok] <= tol_l[ok]).all()
+    assert (spread > 1e-10).sum() <= 0.005 * alpha.size
     # a borderline error norm may flip one accept/reject decision: rare, and
     # the result then still agrees to the integrator's own tolerance
     flipped = valid & ~same_steps
