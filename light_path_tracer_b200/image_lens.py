@@ -284,6 +284,63 @@ class LensPipeline:
                             flags=flags, out=out)
 
 
+class HostFramePipeline:
+    """Host image in -> lensed host frame out, for streams of frames (video, sweeps with a
+    changing background): every frame's source is copied from (pinned) host memory, rendered
+    by the fused kernel and copied back, on ``depth`` CUDA streams with their own device
+    buffers, so frame k+1's host->device copy overlaps frame k's device->host copy (PCIe is
+    full duplex) and the render hides under both.
+
+        pipe = HostFramePipeline((H, W, 3), torch.float32, 40.0, metric)
+        for src, dst in zip(host_sources, host_frames):     # pinned CPU tensors
+            pipe.submit(src, r_obs, out=dst)
+        pipe.synchronize()
+
+    ``rows=(row0, n)`` renders a row tile of the frame (multi-GPU sharding); ``out`` then
+    has n rows."""
+
+    def __init__(self, shape, dtype, vertical_fov_deg=40.0, metric=None, depth=2):
+        t = dev.torch()
+        self.metric = metric if metric is not None else Schwarzschild(M=1.0)
+        self.shape = tuple(shape)
+        self.height, self.width = self.shape[0], self.shape[1]
+        vfov = np.radians(vertical_fov_deg)
+        self.fov = (2 * np.arctan(np.tan(vfov / 2) * self.width / self.height), vfov)
+        device = dev.device()
+        self._slots = [dict(stream=t.cuda.Stream(device=device),
+                            src=t.empty(self.shape, dtype=dtype, device=device), frame=None)
+                       for _ in range(max(1, int(depth)))]
+        self._k = 0
+        self._t = t
+
+    def submit(self, host_src, r_obs, psi=(0.0, 0.0), out=None, rows=None, flags=dev.TRACE_HYBRID, fov=None):
+        """Enqueue one frame; returns the host tensor that will hold it after synchronize()."""
+        t = self._t
+        slot = self._slots[self._k % len(self._slots)]
+        self._k += 1
+        n_rows = self.height if rows is None else rows[1]
+        tile_shape = (n_rows,) + self.shape[1:]
+        if out is None:
+            out = t.empty(tile_shape, dtype=slot["src"].dtype).pin_memory()
+        if slot["frame"] is None or tuple(slot["frame"].shape) != tile_shape:
+            slot["frame"] = t.empty(tile_shape, dtype=slot["src"].dtype, device=slot["src"].device)
+        st = slot["stream"]
+        st.wait_stream(t.cuda.current_stream())
+        with t.cuda.stream(st):
+            slot["src"].copy_(host_src, non_blocking=True)
+            render_frame(slot["src"], self.fov if fov is None else fov, r_obs, self.metric, psi=psi, rows=rows,
+                         flags=flags, out=slot["frame"])
+            out.copy_(slot["frame"], non_blocking=True)
+        return out
+
+    def synchronize(self):
+        """Make the current stream wait for every submitted frame (and block the host)."""
+        cur = self._t.cuda.current_stream()
+        for slot in self._slots:
+            cur.wait_stream(slot["stream"])
+        cur.synchronize()
+
+
 # ============================================================================
 # Benchmark
 # ============================================================================

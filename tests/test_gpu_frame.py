@@ -289,3 +289,25 @@ def test_staged_stores_same_frame(native):
                             flags=dev.TRACE_HYBRID | dev.RENDER_STAGED_STORES)
             assert torch.equal(view, ref[rows[0]:rows[0] + rows[1]])
             assert (big[:shift] == -1).all() and (big[shift + n:] == -1).all()
+
+
+def test_host_frame_pipeline(native, oracle):
+    """HostFramePipeline (pinned host source -> H2D -> fused kernel -> D2H, double-buffered over
+    two streams): every returned frame equals the device-resident render of the same inputs,
+    including when the source changes from frame to frame and for row tiles."""
+    import torch
+    il = _il()
+    metric = _metric(1.0)
+    H, W = 240, 320
+    pipe = il.HostFramePipeline((H, W, 3), torch.float32, 40.0, metric, depth=2)
+    g = torch.Generator().manual_seed(9)
+    sources = [torch.rand(H, W, 3, generator=g).pin_memory() for _ in range(5)]
+    params = [(100.0, (0.0, 0.0)), (30.0, (0.1, 0.0)), (15.0, (0.0, -0.2)), (300.0, (0.05, 0.05)), (100.0, (0.0, 0.0))]
+    outs = [pipe.submit(s, r, psi=p) for s, (r, p) in zip(sources, params)]
+    tile = pipe.submit(sources[0], 100.0, rows=(60, 100))
+    pipe.synchronize()
+    for s, (r, p), o in zip(sources, params, outs):
+        ref = il.render_frame(s.cuda(), pipe.fov, r, metric, psi=p).cpu()
+        assert torch.equal(o, ref)
+    ref = il.render_frame(sources[0].cuda(), pipe.fov, 100.0, metric, rows=(60, 100)).cpu()
+    assert torch.equal(tile, ref)
