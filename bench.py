@@ -337,7 +337,27 @@ def run_gpu(args):
         t_render_strict = float(np.mean(timed(
             lambda: il.render_frame(src, fov, R_OBS, metric, rows=(row0, rows), out=tile, flags=0), args.steps)))
         t_remap = float(np.mean(timed(lambda: il.render_lensed_image(src, a32, fa32, w16, 0.0, fov), args.steps)))
+        # the 8-bit boundary of image_lens.main (uint8 image in, uint8 frame out; LP_DTYPE_U8_UNIT)
+        src8_host = (src_host * 255).to(torch.uint8).pin_memory()
+        pipe8 = il.HostFramePipeline((H, W, 3), torch.uint8, VFOV_DEG, metric, depth=2, unit_u8=True)
+        out8 = [torch.empty((H, W, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        for j in range(4):
+            pipe8.submit(src8_host, R_OBS, out=out8[j % 2], fov=fov)
+        pipe8.synchronize()
+        e8a, e8b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e8a.record()
+        for j in range(args.steps):
+            pipe8.submit(src8_host, R_OBS, out=out8[j % 2], fov=fov)
+        for slot in pipe8._slots:
+            torch.cuda.current_stream().wait_stream(slot["stream"])
+        e8b.record()
+        torch.cuda.synchronize()
+        t_u8 = e8a.elapsed_time(e8b) / args.steps
         extra = {
+            "e2e_u8_io": {"value": H * W / t_u8 * 1e3, "unit": "rays/s", "ms_per_frame": t_u8,
+                          "h2d_bytes_per_step": int(src8_host.numel()), "d2h_bytes_per_step": int(out8[0].numel()),
+                          "path": "as e2e, with the uint8 image boundary of image_lens.main (imread uint8 ... imsave "
+                                  "8 bit): bytes in, bytes out, /255 and trunc(255 v) on the device"},
             "trace_kernel_strict": {"ms": t_strict, "rays_per_s": H * W / t_strict * 1e3,
                                     "tflops": flops_tile / t_strict / 1e9,
                                     "frac_of_measured_fp64_peak": flops_tile / t_strict / 1e9 / peak_tf},

@@ -67,6 +67,12 @@ extern "C" {
 #define LP_DTYPE_U8   0
 #define LP_DTYPE_F32  1
 #define LP_DTYPE_F64  2
+#define LP_DTYPE_U8_UNIT 3        /* uint8 storage standing for float32 value/255: the image as
+                                     image_lens.main handles it end to end (imread uint8 ->
+                                     float32/255, image_lens.py:448-450; imsave float -> 8 bit,
+                                     :510).  Output bytes = trunc(255 * v) of the float32
+                                     pipeline's result v (gathered pixels are the source byte:
+                                     trunc(255 * (k/255.0f)) == k for every k)              */
 
 /* ---- sampling modes for lp_remap ------------------------------------------ */
 #define LP_SAMPLE_NEAREST   0     /* np.rint nearest neighbour: what the reference does

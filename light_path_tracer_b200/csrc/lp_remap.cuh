@@ -15,6 +15,15 @@ template <> __device__ __forceinline__ unsigned char from_f32<unsigned char>(flo
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ double from_f32<double>(float v) { return (double)v; }
 
+// A colour constant (winding colours, magenta) in the image's value range.  scale is 1 except
+// for LP_DTYPE_U8_UNIT images, whose bytes stand for float32 value/255 (image_lens.py:448-450):
+// there the constant c is stored as the byte trunc(c * 255), matplotlib's float -> 8-bit rule.
+template <typename T> __device__ __forceinline__ T colour(float v, float scale) { return from_f32<T>(v); }
+template <> __device__ __forceinline__ unsigned char colour<unsigned char>(float v, float scale)
+{
+    return (unsigned char)__fmul_rn(v, scale);
+}
+
 struct RemapArgs {
     const void *src;
     void *out;
@@ -26,6 +35,7 @@ struct RemapArgs {
     int32_t loop_around;
     int32_t sampling;
     int32_t vec_ok;              // fused kernel: float32 RGB into a 16-byte aligned tile
+    float u8_scale;              // 255 for LP_DTYPE_U8_UNIT images, else 1
 };
 
 // python `a % n` for n > 0
@@ -43,37 +53,6 @@ __device__ __forceinline__ long long pymod(long long a, long long n)
 // (which keep ptxas from interleaving neighbouring pixels' dependency chains) for straight-line
 // code accurate to a few ulp.
 // ---------------------------------------------------------------------------
-// fdlibm kernel polynomials (k_sin.c / k_cos.c), |r| <= pi/4, < 1 ulp
-static __constant__ double c_sin_poly[6] = {-1.66666666666666324348e-01, 8.33333333332248946124e-03,
-                                            -1.98412698298579493134e-04, 2.75573137070700676789e-06,
-                                            -2.50507602534068634195e-08, 1.58969099521155010221e-10};
-static __constant__ double c_cos_poly[6] = {4.16666666666666019037e-02, -1.38888888888741095749e-03,
-                                            2.48015872894767294178e-05, -2.75573143513906633035e-07,
-                                            2.08757232129817482790e-09, -1.13596475577881948265e-11};
-
-// sin and cos of a moderate argument (|x| up to a few pi; the remap passes final_alpha in
-// [0, pi/2]): two-term Cody-Waite reduction by pi/2, the two kernel polynomials, quadrant select.
-__device__ __forceinline__ void sincos_moderate(double x, double &s, double &c)
-{
-    const double shifter = 6755399441055744.0;               // 1.5 * 2^52
-    const double qf = fma(x, 0.63661977236758138, shifter);  // x * 2/pi, rounded to nearest integer
-    const int q = __double2loint(qf);
-    const double n = qf - shifter;
-    double r = fma(-n, 1.5707963267948966, x);               // pi/2 hi
-    r = fma(-n, 6.123233995736766e-17, r);                   // pi/2 lo
-    const double z = r * r;
-    double ps = c_sin_poly[5];
-    double pc = c_cos_poly[5];
-#pragma unroll
-    for (int k = 4; k >= 0; --k) { ps = fma(ps, z, c_sin_poly[k]); pc = fma(pc, z, c_cos_poly[k]); }
-    const double sr = fma(r * z, ps, r);
-    const double cr = fma(z * z, pc, fma(-0.5, z, 1.0));
-    const double s0 = (q & 1) ? cr : sr;
-    const double c0 = (q & 1) ? sr : cr;
-    s = (q & 2) ? -s0 : s0;
-    c = ((q + 1) & 2) ? -c0 : c0;
-}
-
 // Source direction of an escaped pixel -> pinhole plane coordinates (image_lens.py:310-352).
 // Returns front (src_vz > 1e-12) and the continuous source pixel coordinates.
 //
@@ -126,9 +105,9 @@ __device__ __forceinline__ void remap_pixel(const RemapArgs &a, const CamConsts 
     if (fa32 > LP_HALF_PI_F32) {                             // winding false colour, image_lens.py:322-333
         const unsigned k = wnd > 4u ? 4u : wnd;
         if (C == 1) {
-            dst[0] = from_f32<T>(c_wind_luma[k]);
+            dst[0] = colour<T>(c_wind_luma[k], a.u8_scale);
         } else {
-            for (int ch = 0; ch < C; ++ch) dst[ch] = (ch < 3) ? from_f32<T>(c_wind_rgb[k][ch]) : (T)0;
+            for (int ch = 0; ch < C; ++ch) dst[ch] = (ch < 3) ? colour<T>(c_wind_rgb[k][ch], a.u8_scale) : (T)0;
         }
         return;
     }
@@ -145,8 +124,9 @@ __device__ __forceinline__ void remap_pixel(const RemapArgs &a, const CamConsts 
         ok = front && iy >= 0 && iy < H && ix >= 0 && ix < W;
     }
     if (!ok) {                                               // magenta, image_lens.py:381-393
-        if (C == 1) dst[0] = (T)1;
-        else for (int ch = 0; ch < C; ++ch) dst[ch] = (ch == 0 || ch == 2) ? (T)1 : (T)0;
+        const T one = colour<T>(1.0f, a.u8_scale);
+        if (C == 1) dst[0] = one;
+        else for (int ch = 0; ch < C; ++ch) dst[ch] = (ch == 0 || ch == 2) ? one : (T)0;
         return;
     }
     if (a.sampling == LP_SAMPLE_NEAREST) {

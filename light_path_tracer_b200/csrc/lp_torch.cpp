@@ -129,11 +129,12 @@ void build_alpha_lookup(const std::vector<double> &camv, int64_t row0, int64_t r
 }
 
 void remap(const Tensor &src, int64_t channels, const std::vector<double> &camv, const Tensor &fa32, OptTensor w16,
-           bool loop_around, int64_t sampling, int64_t row0, int64_t rows, Tensor out)
+           bool loop_around, int64_t sampling, int64_t row0, int64_t rows, Tensor out, bool unit_u8)
 {
     lp_camera cam = make_cam(camv);
     const int64_t n = rows * (int64_t)cam.width;
-    const int code = dtype_code(src);
+    int code = dtype_code(src);
+    if (unit_u8) { TORCH_CHECK(code == LP_DTYPE_U8, "unit_u8 needs a uint8 image"); code = LP_DTYPE_U8_UNIT; }
     TORCH_CHECK(out.scalar_type() == src.scalar_type(), "out dtype must equal source dtype");
     c10::cuda::CUDAGuard g(src.device());
     check(lp_remap(ptr(src, src.scalar_type(), "src", (int64_t)cam.height * cam.width * channels), code,
@@ -146,11 +147,13 @@ void remap(const Tensor &src, int64_t channels, const std::vector<double> &camv,
 
 void render_frame(const Tensor &src, int64_t channels, const std::vector<double> &camv, int64_t row0, int64_t rows,
                   double M, double R_S, double r_obs, double phi_max, double h_max, bool loop_around,
-                  int64_t sampling, Tensor out, OptTensor fa32, OptTensor w16, OptTensor stats, int64_t flags)
+                  int64_t sampling, Tensor out, OptTensor fa32, OptTensor w16, OptTensor stats, int64_t flags,
+                  bool unit_u8)
 {
     lp_camera cam = make_cam(camv);
     const int64_t n = rows * (int64_t)cam.width;
-    const int code = dtype_code(src);
+    int code = dtype_code(src);
+    if (unit_u8) { TORCH_CHECK(code == LP_DTYPE_U8, "unit_u8 needs a uint8 image"); code = LP_DTYPE_U8_UNIT; }
     TORCH_CHECK(out.scalar_type() == src.scalar_type(), "out dtype must equal source dtype");
     c10::cuda::CUDAGuard g(src.device());
     check(lp_render_frame(ptr(src, src.scalar_type(), "src", (int64_t)cam.height * cam.width * channels), code,

@@ -306,6 +306,8 @@ extern "C" int lp_render_frame(const void *src, int32_t src_dtype, int32_t chann
     ra.row0 = row0; ra.channels = channels; ra.loop_around = render_loop_around; ra.sampling = sampling;
     ra.vec_ok = ((flags & LP_RENDER_STAGED_STORES) && src_dtype == LP_DTYPE_F32 && channels == 3 &&
                  ((uintptr_t)out % 16) == 0) ? 1 : 0;
+    ra.u8_scale = (src_dtype == LP_DTYPE_U8_UNIT) ? 255.0f : 1.0f;
+    if (src_dtype == LP_DTYPE_U8_UNIT) src_dtype = LP_DTYPE_U8;
     cudaStream_t st = (cudaStream_t)stream;
     switch (src_dtype) {
     case LP_DTYPE_U8: return launch_render<unsigned char>(a, ra, c, cam, flags, st);

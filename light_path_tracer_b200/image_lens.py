@@ -202,11 +202,16 @@ def _source_layout(source_image):
 
 def render_lensed_image(source_image, alpha_lookup, final_alpha_lookup, winding_lookup,
                         alpha_crit, fov, render_loop_around=False, psi=(0.0, 0.0), *,
-                        sampling=SAMPLE_NEAREST):
+                        sampling=SAMPLE_NEAREST, unit_u8=False):
     """Deflection -> background remap (image_lens.py:296-397) by lp_remap.  Returns an
     array shaped and typed like ``source_image`` (uint8 / float32 / float64).
     ``alpha_lookup`` and ``alpha_crit`` are accepted and unused, as in the reference.
-    numpy in -> numpy out; CUDA tensors in -> CUDA tensor out."""
+    numpy in -> numpy out; CUDA tensors in -> CUDA tensor out.
+
+    ``unit_u8=True`` (uint8 images only) treats the bytes as float32 value/255 — the 8-bit
+    boundary of ``main()`` (imread -> /255 ... imsave): the result is the byte image
+    ``trunc(255 * render(source/255))``.  Without it a uint8 image behaves as in the
+    reference (colour constants are cast to 0/1)."""
     t = dev.torch()
     e = _lib.ext()
     height, width, channels = _source_layout(source_image)
@@ -231,13 +236,13 @@ def render_lensed_image(source_image, alpha_lookup, final_alpha_lookup, winding_
     out = t.empty_like(src)
     cam = dev.camera_vector((height, width), fov, psi, _psi_frame)
     e.remap(src, channels, cam, fa.contiguous(), None if w is None else w.contiguous(),
-            bool(render_loop_around), int(sampling), 0, height, out)
+            bool(render_loop_around), int(sampling), 0, height, out, bool(unit_u8))
     return out if tensor_in else dev.d2h(out, "frame")
 
 
 def render_frame(source_image, fov, r_obs, metric, psi=(0.0, 0.0), render_loop_around=False, *,
                  sampling=SAMPLE_NEAREST, rows=None, return_lookups=False, stats=None,
-                 flags=dev.TRACE_HYBRID, out=None):
+                 flags=dev.TRACE_HYBRID, out=None, unit_u8=False):
     """Fully fused device-resident frame (lp_render_frame): build_alpha_lookup +
     precompute_final_alpha_lookup + render_lensed_image in ONE launch, bit-identical to
     running the three stages back to back.  ``source_image`` is a CUDA tensor [H,W(,C)];
@@ -260,7 +265,7 @@ def render_frame(source_image, fov, r_obs, metric, psi=(0.0, 0.0), render_loop_a
     cam = dev.camera_vector((height, width), fov, psi, _psi_frame)
     e.render_frame(src, channels, cam, int(row0), int(n_rows), float(metric.M), float(metric.R_S),
                    float(r_obs), dev.PHI_MAX, dev.H_MAX, bool(render_loop_around), int(sampling),
-                   out, fa, w, stats, int(flags))
+                   out, fa, w, stats, int(flags), bool(unit_u8))
     if return_lookups:
         return out, fa, w
     return out
@@ -299,8 +304,9 @@ class HostFramePipeline:
     ``rows=(row0, n)`` renders a row tile of the frame (multi-GPU sharding); ``out`` then
     has n rows."""
 
-    def __init__(self, shape, dtype, vertical_fov_deg=40.0, metric=None, depth=2):
+    def __init__(self, shape, dtype, vertical_fov_deg=40.0, metric=None, depth=2, unit_u8=False):
         t = dev.torch()
+        self.unit_u8 = bool(unit_u8)      # uint8 frames standing for float32/255 (see render_lensed_image)
         self.metric = metric if metric is not None else Schwarzschild(M=1.0)
         self.shape = tuple(shape)
         self.height, self.width = self.shape[0], self.shape[1]
@@ -329,7 +335,7 @@ class HostFramePipeline:
         with t.cuda.stream(st):
             slot["src"].copy_(host_src, non_blocking=True)
             render_frame(slot["src"], self.fov if fov is None else fov, r_obs, self.metric, psi=psi, rows=rows,
-                         flags=flags, out=slot["frame"])
+                         flags=flags, out=slot["frame"], unit_u8=self.unit_u8)
             out.copy_(slot["frame"], non_blocking=True)
         return out
 

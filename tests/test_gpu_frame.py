@@ -311,3 +311,34 @@ def test_host_frame_pipeline(native, oracle):
         assert torch.equal(o, ref)
     ref = il.render_frame(sources[0].cuda(), pipe.fov, 100.0, metric, rows=(60, 100)).cpu()
     assert torch.equal(tile, ref)
+
+
+@pytest.mark.parametrize("tag", ("wide", "offset"))
+def test_unit_u8_boundary(native, golden, oracle, tag):
+    """LP_DTYPE_U8_UNIT: the 8-bit boundary of image_lens.main (imread uint8 -> float32/255 ->
+    pipeline -> imsave 8 bit).  The byte frame must equal trunc(255 * v) of the reference's
+    float32 pipeline on source/255 — exactly, for the remap alone (reference lookups in) and
+    for the fused kernel wherever its float32 final_alpha equals the reference's."""
+    import torch
+    il = _il()
+    g = golden("frames_small.npz")
+    meta = golden("golden_meta.json")["frames"][tag]
+    H, W = meta["H"], meta["W"]
+    fov, psi = (meta["hfov"], meta["vfov"]), tuple(meta["psi"])
+    rng = np.random.default_rng(17)
+    src8 = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    src_f = src8.astype(np.float32) / 255.0                       # image_lens.py:450
+    fa, w = g[tag + "_fa32"], g[tag + "_w16"]
+    ref = (oracle.render_lensed_image(src_f, fa, w, fov, False, psi) * 255).astype(np.uint8)
+    out = il.render_lensed_image(src8, None, fa, w, 0.0, fov, False, psi, unit_u8=True)
+    assert out.dtype == np.uint8 and np.array_equal(out, ref)
+    # plain uint8 keeps the reference's own (0/1 colour) behaviour
+    ref_plain = oracle.render_lensed_image(src8, fa, w, fov, False, psi)
+    assert np.array_equal(il.render_lensed_image(src8, None, fa, w, 0.0, fov, False, psi), ref_plain)
+    # fused
+    metric = _metric(float(meta["M"]))
+    frame, fa_g, w_g = il.render_frame(torch.from_numpy(src8).cuda(), fov, float(meta["r_obs"]), metric, psi=psi,
+                                       unit_u8=True, return_lookups=True)
+    fa_g, w_g = fa_g.cpu().numpy(), w_g.cpu().numpy()
+    ref2 = (oracle.render_lensed_image(src_f, fa_g, w_g, fov, False, psi) * 255).astype(np.uint8)
+    assert np.array_equal(frame.cpu().numpy(), ref2)
