@@ -274,6 +274,36 @@ int lp_schw_rk45_integrate_paths(const double *state0, int64_t n,
                                  int8_t *out_outcome, int32_t *out_nsteps, int8_t *out_status,
                                  void *stream);
 
+/* ---- Kerr tracer (next row after the Schwarzschild path) ------ */
+
+/* Replaces Kerr.trace_rays_batch / _trace_rays_batch_kerr (metrics.py:1128-1132,
+ * :671-679): for every i, _kerr_trace_ray_numba (metrics.py:419-567; Dormand-Prince
+ * 4(5) on the 5-D reduced Hamiltonian state, atol/rtol = 1e-8/1e-6, or 1e-10/1e-8
+ * where axis_refines[i] != 0) from viewing angle alphas[i] and screen angle thetas[i]
+ * for an observer at (r_obs, theta_obs):
+ *     out_fa[i] = final_alpha if the ray escapes else NaN,  out_w[i] = n_half_orbits.
+ * r_plus = M + sqrt(M^2 - a^2) (metrics.py:852); lambda_max = max(5000, 6 r_obs) in the
+ * reference's calls (metrics.py:1120, :1131).  axis_refines (uint8), out_status
+ * (1 / -1 / 0) and out_steps ([n][2]: accepted steps, attempts) are optional. */
+int lp_kerr_trace_batch_f64(const double *alphas, const double *thetas, const uint8_t *axis_refines,
+                            int64_t n, double M, double a, double r_plus, double r_obs,
+                            double theta_obs, double lambda_max,
+                            double *out_fa, int64_t *out_w, int8_t *out_status, int32_t *out_steps,
+                            void *stream);
+
+/* Replaces the tracing part of image_lens.precompute_final_alpha_lookup_2d
+ * (image_lens.py:185-280) for rows [row0, row0+rows): alpha from the float32 table
+ * (tile-relative, rows*width entries), the per-pixel screen angle theta_pixel
+ * (image_lens.py:194-208) evaluated on the device, axis_refine per column
+ * (image_lens.py:210-216; uint8[width], optional), float32 final_alpha and clipped
+ * uint16 winding out (image_lens.py:261-262).  The top/bottom mirror of
+ * image_lens.py:218-220, :272-276 is the caller's (trace the top rows, flip). */
+int lp_kerr_trace_alpha32(const float *alpha32, const lp_camera *h_cam, int32_t row0, int32_t rows,
+                          const uint8_t *axis_refine_cols,
+                          double M, double a, double r_plus, double r_obs, double theta_obs,
+                          double lambda_max, float *out_fa32, uint16_t *out_w16,
+                          int8_t *out_status, int32_t *out_steps, void *stream);
+
 /* ---- measurement helpers --------------------------------------------------- */
 
 /* FP64 pipe micro-benchmark: every thread runs `iters` rounds of 8 independent

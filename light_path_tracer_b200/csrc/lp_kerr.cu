@@ -1,0 +1,428 @@
+// lp_kerr.cu — Kerr null-geodesic tracer: the reference's
+// _kerr_trace_ray_numba (metrics.py:419-567) — Dormand-Prince 4(5) with FSAL and the
+// reference's own step controller on the reduced 5-D Hamiltonian state [r, theta, phi, p_r,
+// p_theta] (metrics.py:227-306), initial conditions metrics.py:148-224, final direction
+// metrics.py:362-416 — batched as _trace_rays_batch_kerr (metrics.py:671-679) and as the
+// per-pixel driver precompute_final_alpha_lookup_2d (image_lens.py:185-280).
+//
+// GPU layout: persistent warps, one ray per LANE, every trip of the main loop is one step
+// ATTEMPT (accepted or rejected) for all 32 lanes; a lane whose ray has ended takes the next
+// ray of its warp's queue as soon as >= KERR_REFILL_MIN lanes are idle (ballot + rank), so
+// captured / escaped rays stop occupying lanes (adaptive step counts differ 3x between
+// neighbouring rays near the shadow edge).  State, the seven stage vectors and the controller
+// live in registers, fp64.  No shared memory, no atomics, no hidden state.
+//
+// Arithmetic: every expression is written in the reference's order and the library is built
+// with -fmad=false, so all +,-,*,/ and sqrt round exactly like the numba build; what differs
+// from the host is the transcendental library (sin/cos of theta in the right-hand side, pow in
+// the controller, arccos at the end), each within 1-2 ulp.
+#include "lp_internal.cuh"
+#include <stdlib.h>
+
+#define KERR_BLOCK 128
+#define KERR_REFILL_MIN 4
+
+struct KerrArgs {
+    // ray source A: explicit arrays
+    const double *alphas, *thetas;
+    const uint8_t *refine;           // optional per-ray axis_refine
+    // ray source B: frame tile (alpha from a float32 table, theta from the pixel)
+    const float *alpha32;            // [rows * width]
+    const uint8_t *refine_cols;      // optional [width]
+    int32_t frame_mode, row0;
+    long long n;
+    double M, a, r_plus, r_obs, theta_obs, lambda_max;
+    // outputs (WIDE: f64 / i64, else f32 / u16)
+    void *out_fa, *out_w;
+    int32_t wide;
+    int8_t *out_status;              // optional
+    int32_t *out_steps;              // optional [n][2]: accepted steps, attempts
+};
+
+static __constant__ double kA21 = 1.0 / 5.0, kA31 = 3.0 / 40.0, kA32 = 9.0 / 40.0, kA41 = 44.0 / 45.0,
+    kA42 = -56.0 / 15.0, kA43 = 32.0 / 9.0, kA51 = 19372.0 / 6561.0, kA52 = -25360.0 / 2187.0,
+    kA53 = 64448.0 / 6561.0, kA54 = -212.0 / 729.0, kA61 = 9017.0 / 3168.0, kA62 = -355.0 / 33.0,
+    kA63 = 46732.0 / 5247.0, kA64 = 49.0 / 176.0, kA65 = -5103.0 / 18656.0, kB1 = 35.0 / 384.0,
+    kB3 = 500.0 / 1113.0, kB4 = 125.0 / 192.0, kB5 = -2187.0 / 6784.0, kB6 = 11.0 / 84.0,
+    kE1 = 71.0 / 57600.0, kE3 = -71.0 / 16695.0, kE4 = 71.0 / 1920.0, kE5 = -17253.0 / 339200.0,
+    kE6 = 22.0 / 525.0, kE7 = -1.0 / 40.0;
+
+// metrics.py:227-306
+__device__ __forceinline__ void kerr_rhs(const double (&s)[5], double p_t, double p_phi, double M, double a,
+                                         double r_floor, double (&out)[5])
+{
+    const double r = s[0], th = s[1], p_r = s[3], p_th = s[4];
+    if (r <= r_floor) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) out[i] = 0.0;
+        return;
+    }
+    double sin_th, cos_th;
+    sincos(th, &sin_th, &cos_th);
+    double sin_th_sq = sin_th * sin_th;
+    if (sin_th_sq < 1e-15) sin_th_sq = 1e-15;
+    const double Sigma = r * r + a * a * cos_th * cos_th;
+    const double Delta = r * r - 2.0 * M * r + a * a;
+    const double A = (r * r + a * a) * (r * r + a * a) - a * a * Delta * sin_th_sq;
+    const double g_tphi_inv = -2.0 * M * a * r / (Sigma * Delta);
+    const double g_rr_inv = Delta / Sigma;
+    const double g_thth_inv = 1.0 / Sigma;
+    const double g_phiphi_inv = (Delta - a * a * sin_th_sq) / (Sigma * Delta * sin_th_sq);
+    const double dr = g_rr_inv * p_r;
+    const double dth = g_thth_inv * p_th;
+    const double dphi = g_tphi_inv * p_t + g_phiphi_inv * p_phi;
+    const double dSigma_dr = 2.0 * r;
+    const double dDelta_dr = 2.0 * r - 2.0 * M;
+    const double dA_dr = 4.0 * r * (r * r + a * a) - a * a * dDelta_dr * sin_th_sq;
+    const double sigma_delta = Sigma * Delta;
+    const double sigma_delta_sq = sigma_delta * sigma_delta;
+    const double dg_tt_inv_dr = (-(dA_dr * sigma_delta - A * (dSigma_dr * Delta + Sigma * dDelta_dr))
+                                 / sigma_delta_sq);
+    const double dg_tphi_inv_dr = (-(2.0 * M * a * (sigma_delta - r * (dSigma_dr * Delta + Sigma * dDelta_dr)))
+                                   / sigma_delta_sq);
+    const double dg_rr_inv_dr = (dDelta_dr * Sigma - Delta * dSigma_dr) / (Sigma * Sigma);
+    const double dg_thth_inv_dr = -dSigma_dr / (Sigma * Sigma);
+    const double den_phi_dr = Sigma * Delta * sin_th_sq;
+    const double dg_phiphi_inv_dr = ((dDelta_dr * den_phi_dr
+                                      - (Delta - a * a * sin_th_sq)
+                                      * (dSigma_dr * Delta + Sigma * dDelta_dr) * sin_th_sq)
+                                     / (den_phi_dr * den_phi_dr));
+    const double dp_r = -0.5 * (dg_tt_inv_dr * p_t * p_t
+                                + 2.0 * dg_tphi_inv_dr * p_t * p_phi
+                                + dg_rr_inv_dr * p_r * p_r
+                                + dg_thth_inv_dr * p_th * p_th
+                                + dg_phiphi_inv_dr * p_phi * p_phi);
+    const double dSigma_dth = -2.0 * a * a * sin_th * cos_th;
+    const double dA_dth = -a * a * Delta * 2.0 * sin_th * cos_th;
+    const double dg_tt_inv_dth = (-(dA_dth * Sigma * Delta - A * dSigma_dth * Delta) / sigma_delta_sq);
+    const double dg_tphi_inv_dth = 2.0 * M * a * r * dSigma_dth / (Sigma * Sigma * Delta);
+    const double dg_rr_inv_dth = -Delta * dSigma_dth / (Sigma * Sigma);
+    const double dg_thth_inv_dth = -dSigma_dth / (Sigma * Sigma);
+    const double num = Delta - a * a * sin_th_sq;
+    const double den = Sigma * Delta * sin_th_sq;
+    const double dnum_dth = -a * a * 2.0 * sin_th * cos_th;
+    const double dden_dth = dSigma_dth * Delta * sin_th_sq + Sigma * Delta * 2.0 * sin_th * cos_th;
+    const double dg_phiphi_inv_dth = (dnum_dth * den - num * dden_dth) / (den * den);
+    const double dp_th = -0.5 * (dg_tt_inv_dth * p_t * p_t
+                                 + 2.0 * dg_tphi_inv_dth * p_t * p_phi
+                                 + dg_rr_inv_dth * p_r * p_r
+                                 + dg_thth_inv_dth * p_th * p_th
+                                 + dg_phiphi_inv_dth * p_phi * p_phi);
+    out[0] = dr; out[1] = dth; out[2] = dphi; out[3] = dp_r; out[4] = dp_th;
+}
+
+// metrics.py:148-224.  false = (ok == False) -> status 0.
+__device__ __forceinline__ bool kerr_init(double M, double a, double r_obs, double alpha, double theta,
+                                          double theta_obs, double (&state)[5], double &p_t, double &p_phi)
+{
+    const double r = r_obs, th = theta_obs;
+    double sin_th, cos_th;
+    sincos(th, &sin_th, &cos_th);
+    double sin_th_sq = sin_th * sin_th;
+    if (sin_th_sq < 1e-15) sin_th_sq = 1e-15;
+    const double Sigma = r * r + a * a * cos_th * cos_th;
+    const double Delta = r * r - 2.0 * M * r + a * a;
+    if (Delta <= 0.0 || Sigma <= 0.0) return false;
+    const double sin_alpha = lp_sin_cr(alpha);
+    double sin_screen, cos_screen;
+    sincos(theta, &sin_screen, &cos_screen);
+    const double E = 1.0;
+    const double sqrt_Delta = __dsqrt_rn(Delta), sqrt_Sigma = __dsqrt_rn(Sigma);
+    const double rho = r * sin_alpha * sqrt_Sigma / sqrt_Delta;
+    const double alpha_screen = -rho * sin_screen;
+    const double beta_screen = -rho * cos_screen;
+    const double xi = -alpha_screen * sin_th;
+    const double eta = beta_screen * beta_screen + cos_th * cos_th * (alpha_screen * alpha_screen - a * a);
+    const double L = xi * E;
+    const double Q = eta * E * E;
+    p_t = -E;
+    p_phi = L;
+    double Theta = Q - cos_th * cos_th * (L * L / sin_th_sq - a * a * E * E);
+    if (Theta < 0.0) Theta = 0.0;
+    const double p_th_sign = (cos_screen > 0.0) ? -1.0 : 1.0;
+    const double p_theta = p_th_sign * __dsqrt_rn(Theta);
+    const double A_val = (r * r + a * a) * (r * r + a * a) - a * a * Delta * sin_th_sq;
+    const double g_tt_inv = -A_val / (Sigma * Delta);
+    const double g_tphi_inv = -2.0 * M * a * r / (Sigma * Delta);
+    const double g_rr_inv = Delta / Sigma;
+    const double g_thth_inv = 1.0 / Sigma;
+    const double g_phiphi_inv = (Delta - a * a * sin_th_sq) / (Sigma * Delta * sin_th_sq);
+    const double other = (g_tt_inv * p_t * p_t
+                          + 2.0 * g_tphi_inv * p_t * p_phi
+                          + g_thth_inv * p_theta * p_theta
+                          + g_phiphi_inv * p_phi * p_phi);
+    double p_r_sq = -other / g_rr_inv;
+    if (p_r_sq < 0.0) p_r_sq = 0.0;
+    state[0] = r; state[1] = th; state[2] = 0.0; state[3] = -__dsqrt_rn(p_r_sq); state[4] = p_theta;
+    return true;
+}
+
+// metrics.py:362-416
+__device__ __noinline__ int kerr_extract_angle(const double (&state)[5], double p_t, double p_phi, double M, double a,
+                                               double r_capture, int event_status, double &fa, long long &nh)
+{
+    const double r_f = state[0], th_f = state[1], phi_f = state[2], p_r_f = state[3], p_th_f = state[4];
+    const long long n_half = half_orbits(phi_f);
+    fa = __longlong_as_double(0x7ff8000000000000LL);
+    if (r_f <= r_capture * 1.1 || event_status == -1) { nh = n_half; return -1; }
+    if (!isfinite(r_f) || !isfinite(th_f) || !isfinite(phi_f)) { nh = 0; return 0; }
+    double sin_th, cos_th;
+    sincos(th_f, &sin_th, &cos_th);
+    double sin_th_sq = sin_th * sin_th;
+    if (sin_th_sq < 1e-15) sin_th_sq = 1e-15;
+    const double Sigma_f = r_f * r_f + a * a * cos_th * cos_th;
+    const double Delta_f = r_f * r_f - 2.0 * M * r_f + a * a;
+    nh = n_half;
+    if (Sigma_f <= 1e-15 || fabs(Delta_f) <= 1e-15) return 0;
+    const double dr_dl = Delta_f / Sigma_f * p_r_f;
+    const double dth_dl = p_th_f / Sigma_f;
+    const double dphi_dl = (-2.0 * M * a * r_f / (Sigma_f * Delta_f) * p_t
+                            + (Delta_f - a * a * sin_th_sq) / (Sigma_f * Delta_f * sin_th_sq) * p_phi);
+    double sin_phi, cos_phi;
+    sincos(phi_f, &sin_phi, &cos_phi);
+    const double vx = (sin_th * cos_phi * dr_dl + r_f * cos_th * cos_phi * dth_dl - r_f * sin_th * sin_phi * dphi_dl);
+    const double vy = (sin_th * sin_phi * dr_dl + r_f * cos_th * sin_phi * dth_dl + r_f * sin_th * cos_phi * dphi_dl);
+    const double vz = cos_th * dr_dl - r_f * sin_th * dth_dl;
+    if (!isfinite(vx) || !isfinite(vy) || !isfinite(vz)) return 0;
+    const double v_mag = __dsqrt_rn(vx * vx + vy * vy + vz * vz);
+    if (v_mag < 1e-30) return 1;
+    fa = acos(clip_scalar(-vx / v_mag, -1.0, 1.0));
+    return 1;
+}
+
+__device__ __forceinline__ bool finite5(const double (&x)[5])
+{
+    return isfinite(x[0]) && isfinite(x[1]) && isfinite(x[2]) && isfinite(x[3]) && isfinite(x[4]);
+}
+
+// image_lens.py:194-208: screen angle of a pixel (theta_pixel)
+__device__ __forceinline__ double pixel_theta(const CamConsts &cam, int row, int col)
+{
+    const double xc = cam_x(cam, col), yc = cam_y(cam, row);
+    const double denom = __dsqrt_rn(1.0 + xc * xc + yc * yc);
+    const double vx = xc / denom, vy = yc / denom, vz = 1.0 / denom;
+    return atan2(vx * cam.ex0 + vy * cam.ex1 + vz * cam.ex2, vx * cam.ey0 + vy * cam.ey1 + vz * cam.ey2);
+}
+
+__global__ void __launch_bounds__(KERR_BLOCK, 2)
+lp_kerr_kernel(const KerrArgs a, const CamConsts cam)
+{
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const double M = a.M, sp = a.a, r_floor = a.r_plus * 1.001;
+    const double r_capture = a.r_plus * 1.01, r_escape = a.r_obs * 2.0, lambda_max = a.lambda_max;
+    const double h_min = 1e-12;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+
+    bool active = false;
+    long long idx = -1;
+    double state[5], k1[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) { state[i] = 0.0; k1[i] = 0.0; }
+    double p_t = -1.0, p_phi = 0.0, lam = 0.0, h = 1.0, atol = 1e-8, rtol = 1e-6;
+    int accepted = 0, attempts = 0, iters = 0;
+
+    long long cursor = 0;
+    bool queue_empty = (warp_id * 32 >= a.n);
+
+    while (true) {
+        // ---------------- lane refill ----------------
+        const unsigned idle = __ballot_sync(full, !active);
+        if (idle && !queue_empty && (__popc(idle) >= KERR_REFILL_MIN || idle == full)) {
+            const int rank = __popc(idle & ((1u << lane) - 1u));
+            const long long v = cursor + rank;
+            const long long ray = ((v >> 5) * n_warps + warp_id) * 32 + (v & 31);
+            cursor += __popc(idle);
+            if (((cursor >> 5) * n_warps + warp_id) * 32 + (cursor & 31) >= a.n) queue_empty = true;
+            if (!active && ray < a.n) {
+                idx = ray;
+                double alpha, theta;
+                bool refine;
+                if (a.frame_mode) {
+                    int row, col;
+                    pixel_row_col(ray, a.n, cam.width, a.row0, row, col);
+                    alpha = (double)__ldg(a.alpha32 + ray);                 // image_lens.py:247
+                    theta = pixel_theta(cam, row, col);
+                    refine = a.refine_cols ? (__ldg(a.refine_cols + col) != 0) : false;
+                } else {
+                    alpha = __ldg(a.alphas + ray);
+                    theta = __ldg(a.thetas + ray);
+                    refine = a.refine ? (__ldg(a.refine + ray) != 0) : false;
+                }
+                atol = refine ? 1e-10 : 1e-8;                               // metrics.py:432-433
+                rtol = refine ? 1e-8 : 1e-6;
+                if (kerr_init(M, sp, a.r_obs, alpha, theta, a.theta_obs, state, p_t, p_phi)) {
+                    kerr_rhs(state, p_t, p_phi, M, sp, r_floor, k1);        // FSAL seed, metrics.py:447
+                    lam = 0.0;
+                    h = fmax(1.0, 0.01 * a.r_obs);
+                    accepted = 0; attempts = 0; iters = 0;
+                    active = true;
+                } else {
+                    if (a.wide) { ((double *)a.out_fa)[idx] = qnan; ((long long *)a.out_w)[idx] = 0; }
+                    else { ((float *)a.out_fa)[idx] = (float)qnan; ((unsigned short *)a.out_w)[idx] = 0; }
+                    if (a.out_status) a.out_status[idx] = 0;
+                    if (a.out_steps) { a.out_steps[2 * idx] = 0; a.out_steps[2 * idx + 1] = 0; }
+                }
+            }
+        }
+        if (!__any_sync(full, active)) {
+            if (queue_empty) break;
+            continue;
+        }
+        if (!active) continue;
+
+        // ---------------- one trip of the reference's `for _step in range(max_steps)` ----------------
+        int done = 0;            // 0 running, 1 finished -> extract angle, 2 invalid (status 0)
+        int event_status = 2;
+        if (iters >= 200000 || lam >= lambda_max) {
+            done = 1;
+        } else {
+            iters++;
+            const double remaining = lambda_max - lam;
+            if (h > remaining) h = remaining;
+            if (h <= 0.0) {
+                done = 1;
+            } else {
+                attempts++;
+                double k2[5], k3[5], k4[5], k5[5], k6[5], k7[5], tmp[5], nxt[5];
+#pragma unroll
+                for (int i = 0; i < 5; ++i) tmp[i] = state[i] + h * kA21 * k1[i];
+                kerr_rhs(tmp, p_t, p_phi, M, sp, r_floor, k2);
+#pragma unroll
+                for (int i = 0; i < 5; ++i) tmp[i] = state[i] + h * (kA31 * k1[i] + kA32 * k2[i]);
+                kerr_rhs(tmp, p_t, p_phi, M, sp, r_floor, k3);
+#pragma unroll
+                for (int i = 0; i < 5; ++i) tmp[i] = state[i] + h * (kA41 * k1[i] + kA42 * k2[i] + kA43 * k3[i]);
+                kerr_rhs(tmp, p_t, p_phi, M, sp, r_floor, k4);
+#pragma unroll
+                for (int i = 0; i < 5; ++i)
+                    tmp[i] = state[i] + h * (kA51 * k1[i] + kA52 * k2[i] + kA53 * k3[i] + kA54 * k4[i]);
+                kerr_rhs(tmp, p_t, p_phi, M, sp, r_floor, k5);
+#pragma unroll
+                for (int i = 0; i < 5; ++i)
+                    tmp[i] = state[i] + h * (kA61 * k1[i] + kA62 * k2[i] + kA63 * k3[i] + kA64 * k4[i] + kA65 * k5[i]);
+                kerr_rhs(tmp, p_t, p_phi, M, sp, r_floor, k6);
+#pragma unroll
+                for (int i = 0; i < 5; ++i)
+                    nxt[i] = state[i] + h * (kB1 * k1[i] + kB3 * k3[i] + kB4 * k4[i] + kB5 * k5[i] + kB6 * k6[i]);
+                kerr_rhs(nxt, p_t, p_phi, M, sp, r_floor, k7);
+
+                if (!finite5(nxt) || nxt[0] <= 0.0) {                        // metrics.py:498-503
+                    h *= 0.25;
+                    if (h < h_min) done = 2;
+                } else {
+                    double err_sq = 0.0;
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) {
+                        const double ei = h * (kE1 * k1[i] + kE3 * k3[i] + kE4 * k4[i] + kE5 * k5[i] + kE6 * k6[i]
+                                               + kE7 * k7[i]);
+                        const double sc = atol + rtol * fmax(fabs(state[i]), fabs(nxt[i]));
+                        const double q = ei / sc;
+                        err_sq += q * q;
+                    }
+                    const double err_norm = __dsqrt_rn(err_sq / 5.0);
+                    if (err_norm > 1.0) {                                    // reject, metrics.py:516-522
+                        const double factor = fmax(0.2, 0.9 * pow(err_norm, -0.2));
+                        h *= factor;
+                        if (h < h_min) done = 2;
+                    } else {
+                        accepted++;
+                        const double r_prev = state[0], r_next = nxt[0];
+                        const bool cap = (r_prev > r_capture && r_next <= r_capture);
+                        const bool esc = !cap && (r_prev < r_escape && r_next >= r_escape);
+                        if (cap || esc) {                                    // metrics.py:528-550
+                            const double target = cap ? r_capture : r_escape;
+                            const double denom = r_next - r_prev;
+                            double frac = (denom == 0.0) ? 1.0 : (target - r_prev) / denom;
+                            frac = clip_scalar(frac, 0.0, 1.0);
+#pragma unroll
+                            for (int i = 0; i < 5; ++i) state[i] = state[i] + frac * (nxt[i] - state[i]);
+                            lam += frac * h;
+                            event_status = cap ? -1 : 1;
+                            done = 1;
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 5; ++i) { state[i] = nxt[i]; k1[i] = k7[i]; }
+                            lam += h;
+                            if (!finite5(state)) {
+                                done = 2;
+                            } else if (err_norm < 1e-10) {
+                                h *= 5.0;
+                            } else {
+                                h *= fmin(5.0, 0.9 * pow(err_norm, -0.2));
+                            }
+                        }
+                    }
+                }
+            }
+        }
+
+        if (done) {
+            double fa = qnan;
+            long long nh = 0;
+            int status = 0;
+            if (done == 1) status = kerr_extract_angle(state, p_t, p_phi, M, sp, r_capture, event_status, fa, nh);
+            const double fa_out = (status == 1) ? fa : qnan;                 // metrics.py:678
+            if (a.wide) {
+                ((double *)a.out_fa)[idx] = fa_out;
+                ((long long *)a.out_w)[idx] = nh;
+            } else {
+                ((float *)a.out_fa)[idx] = (float)fa_out;                    // image_lens.py:261
+                const long long c = nh < 0 ? 0 : (nh > 65535 ? 65535 : nh);  // image_lens.py:262
+                ((unsigned short *)a.out_w)[idx] = (unsigned short)c;
+            }
+            if (a.out_status) a.out_status[idx] = (int8_t)status;
+            if (a.out_steps) { a.out_steps[2 * idx] = accepted; a.out_steps[2 * idx + 1] = attempts; }
+            active = false;
+        }
+    }
+}
+
+static int kerr_launch(KerrArgs &a, const CamConsts &cam, cudaStream_t stream)
+{
+    if (a.n == 0) return LP_OK;
+    int grid = 0;
+    int rc = lp_grid_for((const void *)lp_kerr_kernel, KERR_BLOCK, &grid);
+    if (rc != LP_OK) return rc;
+    const long long chunks = (a.n + KERR_BLOCK - 1) / KERR_BLOCK;
+    if (chunks < grid) grid = (int)chunks;
+    lp_kerr_kernel<<<grid, KERR_BLOCK, 0, stream>>>(a, cam);
+    return lp_check_launch();
+}
+
+extern "C" int lp_kerr_trace_batch_f64(const double *alphas, const double *thetas, const uint8_t *axis_refines,
+                                       int64_t n, double M, double a, double r_plus, double r_obs,
+                                       double theta_obs, double lambda_max,
+                                       double *out_fa, int64_t *out_w, int8_t *out_status, int32_t *out_steps,
+                                       void *stream)
+{
+    if (n < 0) return LP_ERR_INVALID_ARG;
+    if (n > 0 && (!alphas || !thetas || !out_fa || !out_w)) return LP_ERR_INVALID_ARG;
+    KerrArgs k = {};
+    k.alphas = alphas; k.thetas = thetas; k.refine = axis_refines; k.n = n;
+    k.M = M; k.a = a; k.r_plus = r_plus; k.r_obs = r_obs; k.theta_obs = theta_obs; k.lambda_max = lambda_max;
+    k.out_fa = out_fa; k.out_w = out_w; k.wide = 1; k.out_status = out_status; k.out_steps = out_steps;
+    CamConsts cam = {};
+    return kerr_launch(k, cam, (cudaStream_t)stream);
+}
+
+extern "C" int lp_kerr_trace_alpha32(const float *alpha32, const lp_camera *h_cam, int32_t row0, int32_t rows,
+                                     const uint8_t *axis_refine_cols,
+                                     double M, double a, double r_plus, double r_obs, double theta_obs,
+                                     double lambda_max, float *out_fa32, uint16_t *out_w16,
+                                     int8_t *out_status, int32_t *out_steps, void *stream)
+{
+    CamConsts cam;
+    int rc = lp_make_cam_consts(h_cam, &cam);
+    if (rc != LP_OK) return rc;
+    if (row0 < 0 || rows < 0 || (long long)row0 + rows > cam.height) return LP_ERR_INVALID_ARG;
+    const long long n = (long long)rows * cam.width;
+    if (n > 0 && (!alpha32 || !out_fa32 || !out_w16)) return LP_ERR_INVALID_ARG;
+    KerrArgs k = {};
+    k.alpha32 = alpha32; k.refine_cols = axis_refine_cols; k.frame_mode = 1; k.row0 = row0; k.n = n;
+    k.M = M; k.a = a; k.r_plus = r_plus; k.r_obs = r_obs; k.theta_obs = theta_obs; k.lambda_max = lambda_max;
+    k.out_fa = out_fa32; k.out_w = out_w16; k.wide = 0; k.out_status = out_status; k.out_steps = out_steps;
+    return kerr_launch(k, cam, (cudaStream_t)stream);
+}

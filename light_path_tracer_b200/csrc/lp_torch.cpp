@@ -250,6 +250,41 @@ void rk45_integrate_paths(const Tensor &state0, double M, double R_S, double lam
           "lp_schw_rk45_integrate_paths");
 }
 
+void kerr_trace_batch(const Tensor &alphas, const Tensor &thetas, OptTensor refine, double M, double a, double r_plus,
+                      double r_obs, double theta_obs, double lambda_max, Tensor out_fa, Tensor out_w,
+                      OptTensor status, OptTensor steps)
+{
+    const int64_t n = alphas.numel();
+    c10::cuda::CUDAGuard g(alphas.device());
+    check(lp_kerr_trace_batch_f64((const double *)ptr(alphas, c10::ScalarType::Double, "alphas", 0),
+                                  (const double *)ptr(thetas, c10::ScalarType::Double, "thetas", n),
+                                  (const uint8_t *)optptr(refine, c10::ScalarType::Byte, "axis_refines", n), n, M, a,
+                                  r_plus, r_obs, theta_obs, lambda_max,
+                                  (double *)ptr(out_fa, c10::ScalarType::Double, "out_fa", n),
+                                  (int64_t *)ptr(out_w, c10::ScalarType::Long, "out_w", n),
+                                  (int8_t *)optptr(status, c10::ScalarType::Char, "status", n),
+                                  (int32_t *)optptr(steps, c10::ScalarType::Int, "steps", 2 * n), stream_of(alphas)),
+          "lp_kerr_trace_batch_f64");
+}
+
+void kerr_trace_alpha32(const Tensor &alpha32, const std::vector<double> &camv, int64_t row0, int64_t rows,
+                        OptTensor refine_cols, double M, double a, double r_plus, double r_obs, double theta_obs,
+                        double lambda_max, Tensor out_fa32, Tensor out_w16, OptTensor status, OptTensor steps)
+{
+    lp_camera cam = make_cam(camv);
+    const int64_t n = rows * (int64_t)cam.width;
+    c10::cuda::CUDAGuard g(alpha32.device());
+    check(lp_kerr_trace_alpha32((const float *)ptr(alpha32, c10::ScalarType::Float, "alpha32", n), &cam, (int32_t)row0,
+                                (int32_t)rows,
+                                (const uint8_t *)optptr(refine_cols, c10::ScalarType::Byte, "axis_refine_cols", cam.width),
+                                M, a, r_plus, r_obs, theta_obs, lambda_max,
+                                (float *)ptr(out_fa32, c10::ScalarType::Float, "out_fa32", n),
+                                (uint16_t *)ptr(out_w16, c10::ScalarType::UInt16, "out_w16", n),
+                                (int8_t *)optptr(status, c10::ScalarType::Char, "status", n),
+                                (int32_t *)optptr(steps, c10::ScalarType::Int, "steps", 2 * n), stream_of(alpha32)),
+          "lp_kerr_trace_alpha32");
+}
+
 void bench_dfma(int64_t blocks, int64_t threads, int64_t iters, Tensor sink)
 {
     c10::cuda::CUDAGuard g(sink.device());
@@ -290,5 +325,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.def("rk45_trace_batch", &rk45_trace_batch);
     m.def("rk45_trace_paths", &rk45_trace_paths);
     m.def("rk45_integrate_paths", &rk45_integrate_paths);
+    m.def("kerr_trace_batch", &kerr_trace_batch);
+    m.def("kerr_trace_alpha32", &kerr_trace_alpha32);
     m.def("bench_dfma", &bench_dfma);
 }

@@ -179,12 +179,100 @@ def precompute_final_alpha_lookup(alpha_lookup, alpha_crit, r_obs, metric):
     return fa_out, w_out, n, n
 
 
+def _axis_refine_columns(width, fx, psi):
+    """Columns within Y_AXIS_REFINE_FRAC of the BH's screen column get the tighter integrator
+    tolerances (image_lens.py:210-216)."""
+    x_cam = (np.arange(width) - width / 2) / fx
+    _, bh_x_cam, in_front = _psi_to_cam_projection(psi)
+    if not in_front:
+        return np.zeros(width, dtype=bool)
+    x_rel = x_cam - bh_x_cam
+    x_abs_max = max(float(np.max(np.abs(x_rel))), 1e-12)
+    return np.abs(x_rel) <= (Y_AXIS_REFINE_FRAC * x_abs_max)
+
+
+def _theta_pixel(image_dimension, fov, psi, rows):
+    """Screen angle of every pixel of the first `rows` rows (image_lens.py:194-208), host numpy —
+    only used for plug-in metrics that are not served by the CUDA Kerr kernel."""
+    height, width = image_dimension
+    fx, fy = _focal(image_dimension, fov)
+    x_cam = (np.arange(width) - width / 2) / fx
+    y_cam = (np.arange(rows) - height / 2) / fy
+    _, e_x, e_y, _ = _psi_frame(psi)
+    denom = np.sqrt(1.0 + x_cam[None, :]**2 + y_cam[:, None]**2)
+    vx, vy, vz = x_cam[None, :] / denom, y_cam[:, None] / denom, 1.0 / denom
+    return np.arctan2(vx * e_x[0] + vy * e_x[1] + vz * e_x[2], vx * e_y[0] + vy * e_y[1] + vz * e_y[2])
+
+
 def precompute_final_alpha_lookup_2d(alpha_lookup, fov, alpha_crit, r_obs, metric,
                                      theta_obs=np.pi / 2, psi=(0.0, 0.0)):
-    """Kerr-only (alpha, theta) lookup (image_lens.py:185-280): OUT OF SCOPE here
-    (SURVEY.md §8(f) rank 1 — next after the Schwarzschild path)."""
-    raise NotImplementedError("precompute_final_alpha_lookup_2d serves Kerr metrics only; "
-                              "the B200 path covers Schwarzschild")
+    """One ray per pixel for metrics without spherical symmetry (image_lens.py:185-280):
+    -> (final_alpha float32[H,W], winding uint16[H,W], total_rays, traced_rays).
+
+    Per pixel the ray is launched at viewing angle alpha and screen angle theta_pixel; the
+    columns around the BH's screen column are traced with tighter tolerances (axis_refine); an
+    equatorial observer with psi_y = 0 traces the top half only and mirrors it.  A ``Kerr``
+    metric takes the single-launch GPU path (lp_kerr_trace_alpha32: theta_pixel is evaluated on
+    the device); any other metric is driven through its own 7-argument ``trace_rays_batch`` in
+    50 000-ray chunks exactly like the reference."""
+    tensor_in = _is_tensor(alpha_lookup)
+    shape = tuple(alpha_lookup.shape)
+    height, width = shape
+    fx, _ = _focal(shape, fov)
+    refine_cols = _axis_refine_columns(width, fx, psi)
+    use_tb_symmetry = bool(np.isclose(theta_obs, np.pi / 2) and np.isclose(psi[0], 0.0))
+    trace_rows = (height + 1) // 2 if use_tb_symmetry else height
+    n_traced = trace_rows * width
+    if use_tb_symmetry:
+        print(f"  tracing {n_traced:,} rays with top/bottom symmetry ({height * width:,} pixels total)")
+    else:
+        print(f"  tracing {n_traced:,} rays ({height * width:,} pixels total)")
+
+    if isinstance(metric, Kerr) and type(metric).trace_rays_batch is Kerr.trace_rays_batch:
+        t = dev.torch()
+        if tensor_in:
+            a32 = alpha_lookup[:trace_rows].to(t.float32).contiguous()
+        else:
+            a32 = dev.h2d(np.ascontiguousarray(np.asarray(alpha_lookup, dtype=np.float32)[:trace_rows]), "alpha")
+        fa_out = t.full(shape, float("nan"), dtype=t.float32, device=a32.device)
+        w_out = t.zeros(shape, dtype=t.uint16, device=a32.device)
+        if n_traced:
+            cam = dev.camera_vector(shape, fov, psi, _psi_frame)
+            d_cols = dev.h2d(refine_cols.astype(np.uint8), "refine_cols")
+            fa, w = metric.trace_alpha_table_2d(a32, cam, r_obs, theta_obs, row0=0, refine_cols=d_cols)
+            fa_out[:trace_rows] = fa
+            w_out[:trace_rows] = w
+        if use_tb_symmetry:
+            top_half = height // 2
+            if top_half > 0:                                 # image_lens.py:272-276
+                fa_out[height - top_half:] = fa_out[:top_half].flip(0)
+                w_out.view(t.int16)[height - top_half:] = w_out.view(t.int16)[:top_half].flip(0)
+        if tensor_in:
+            return fa_out, w_out, height * width, n_traced
+        return dev.d2h(fa_out, "fa32"), dev.d2h(w_out, "w16"), height * width, n_traced
+
+    # plug-in metric: the reference's own chunked host driver
+    a_np = dev.d2h(alpha_lookup) if tensor_in else np.asarray(alpha_lookup)
+    alpha_f64 = a_np[:trace_rows, :].ravel().astype(np.float64)
+    theta_f64 = _theta_pixel(shape, fov, psi, trace_rows).ravel().astype(np.float64)
+    axis_flat = np.broadcast_to(refine_cols[None, :], (trace_rows, width)).ravel().astype(np.bool_)
+    fa_buf = np.full(alpha_f64.size, np.nan, dtype=np.float64)
+    w_buf = np.zeros(alpha_f64.size, dtype=np.int64)
+    chunk = 50_000
+    for start in range(0, alpha_f64.size, chunk):
+        end = min(start + chunk, alpha_f64.size)
+        metric.trace_rays_batch(r_obs, alpha_f64[start:end], theta_f64[start:end], theta_obs,
+                                axis_flat[start:end], fa_buf[start:end], w_buf[start:end])
+    fa_out = np.full(shape, np.nan, dtype=np.float32)
+    w_out = np.zeros(shape, dtype=WINDING_DTYPE)
+    fa_out[:trace_rows] = fa_buf.astype(np.float32).reshape(trace_rows, width)
+    w_out[:trace_rows] = np.clip(w_buf, 0, WINDING_MAX).astype(WINDING_DTYPE).reshape(trace_rows, width)
+    if use_tb_symmetry:
+        top_half = height // 2
+        if top_half > 0:
+            fa_out[height - top_half:] = fa_out[:top_half][::-1]
+            w_out[height - top_half:] = w_out[:top_half][::-1]
+    return fa_out, w_out, height * width, n_traced
 
 
 # ============================================================================
@@ -428,17 +516,19 @@ def main(metric=None, M=1.0, a=0.0, r_obs_mult=100.0, psi=(0.0, 0.0), vertical_f
     print(f"BH screen offset: psi_y={np.degrees(psi_y):.4f} deg, "
           f"psi_x={np.degrees(psi_x):.4f} deg ({where})")
 
-    if not metric.is_spherically_symmetric:
-        raise NotImplementedError("only spherically symmetric metrics are served by the B200 path")
-
-    print("Building per-pixel alpha lookup...")
+    print("Building per-pixel alpha lookup..." if metric.is_spherically_symmetric
+          else "Building per-pixel (alpha, theta) lookup...")
     stage_start = perf_counter()
     alpha_lookup = build_alpha_lookup((height, width), fov, psi=psi)
     timings["build_lookup"] = perf_counter() - stage_start
 
     stage_start = perf_counter()
-    final_alpha_lookup, winding_lookup, total_rays, traced_rays = precompute_final_alpha_lookup(
-        alpha_lookup, alpha_crit, r_obs, metric)
+    if metric.is_spherically_symmetric:                       # image_lens.py:477-498
+        final_alpha_lookup, winding_lookup, total_rays, traced_rays = precompute_final_alpha_lookup(
+            alpha_lookup, alpha_crit, r_obs, metric)
+    else:
+        final_alpha_lookup, winding_lookup, total_rays, traced_rays = precompute_final_alpha_lookup_2d(
+            alpha_lookup, fov, alpha_crit, r_obs, metric, psi=psi)
     timings["precompute"] = perf_counter() - stage_start
 
     stage_start = perf_counter()

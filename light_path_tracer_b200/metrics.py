@@ -179,29 +179,209 @@ class Schwarzschild(Metric):
 
 
 class Kerr(Metric):
-    """Rotating black hole.  OUT OF SCOPE for this build (SURVEY.md §8(f) rank 1: next);
-    the name exists because the reference's image_lens imports it (image_lens.py:9)."""
+    """Rotating black hole in Boyer-Lindquist coordinates, spin ``a`` with ``|a| <= M``
+    (reference: metrics.py:840-1132).  Ray tracing (``trace_ray``, ``trace_rays_batch``) runs in
+    the CUDA kernel lp_kerr_kernel (csrc/lp_kerr.cu: the reference's Dormand-Prince 4(5)
+    integrator on the reduced 5-D Hamiltonian state); the closed-form helpers are host
+    arithmetic."""
 
     is_spherically_symmetric = False
 
     def __init__(self, M=1.0, a=0.0):
         if abs(a) > M:
-            raise ValueError(f"|a| must be <= M (got a={a}, M={M})")   # metrics.py:849-850
-        raise NotImplementedError(
-            "Kerr tracing is not part of the B200 hot path yet (Schwarzschild only)")
+            raise ValueError(f"|a|={abs(a)} exceeds M={M}")              # metrics.py:849-850
+        self.M = M
+        self.a = a
+        self.r_plus = M + np.sqrt(M**2 - a**2)                            # outer horizon
+
+    def _Sigma(self, r, th):
+        return r**2 + self.a**2 * np.cos(th)**2
+
+    def _Delta(self, r):
+        return r**2 - 2 * self.M * r + self.a**2
+
+    def capture_radius(self):
+        return self.r_plus * 1.01
+
+    # -- spherical photon orbits (metrics.py:864-891) ----------------------------------
+    def _unstable_photon_r(self):
+        """(prograde, retrograde) circular photon orbit radii — Bardeen's formula."""
+        M, a = self.M, self.a
+        if a == 0:
+            return 3 * M, 3 * M
+        return (2 * M * (1 + np.cos(2 / 3 * np.arccos(-a / M))),
+                2 * M * (1 + np.cos(2 / 3 * np.arccos(a / M))))
+
+    def _xi_eta(self, r_ph):
+        """Conserved (xi, eta) of the spherical photon orbit of radius r_ph."""
+        M, a = self.M, self.a
+        Delta = self._Delta(r_ph)
+        xi = ((r_ph**2 + a**2) / a - 2 * r_ph * Delta / (a * (r_ph - M)))
+        eta = (r_ph**3 / (a**2 * (r_ph - M)**2) * (4 * M * Delta - r_ph * (r_ph - M)**2))
+        return xi, eta
+
+    def _critical_impact_params(self):
+        if self.a == 0:
+            raise ValueError("_critical_impact_params undefined for a=0")
+        return [self._xi_eta(r_ph) for r_ph in self._unstable_photon_r()]
+
+    def alpha_crit(self, r_obs, theta_obs=np.pi / 2):
+        """Conservative shadow envelope: the largest impact parameter over 50 sampled spherical
+        photon orbits, never below the Schwarzschild value (metrics.py:893-930)."""
+        M, a = self.M, self.a
+        if a == 0:
+            arg = 3 * np.sqrt(3) * M * np.sqrt(1 - 2 * M / r_obs) / r_obs
+            return np.arcsin(np.clip(arg, -1.0, 1.0))
+        r_pro, r_ret = self._unstable_photon_r()
+        b2_max = 0.0
+        for r_ph in np.linspace(r_pro, r_ret, 50):
+            xi, eta = self._xi_eta(r_ph)
+            b2_max = max(b2_max, xi**2 + max(eta, 0.0))
+        b_crit = max(np.sqrt(b2_max), 3 * np.sqrt(3) * M)
+        Delta_obs, Sigma_obs = self._Delta(r_obs), self._Sigma(r_obs, theta_obs)
+        A = (r_obs**2 + a**2)**2 - a**2 * Delta_obs * np.sin(theta_obs)**2
+        arg = b_crit * np.sqrt(Sigma_obs * Delta_obs / A) / r_obs
+        return np.arcsin(np.clip(arg, -1.0, 1.0))
+
+    def viewing_angle_to_impact_parameter(self, alpha, r_obs, theta_obs=np.pi / 2):
+        if self.a == 0:
+            return r_obs * np.sin(alpha) / np.sqrt(1 - 2 * self.M / r_obs)
+        Delta, Sigma = self._Delta(r_obs), self._Sigma(r_obs, theta_obs)
+        A = (r_obs**2 + self.a**2)**2 - self.a**2 * Delta * np.sin(theta_obs)**2
+        return r_obs * np.sin(alpha) * np.sqrt(A / (Sigma * Delta))
+
+    # -- inverse metric and its r / theta derivatives, shared by the two host functions --------
+    def _inverse_metric(self, r, th):
+        M, a = self.M, self.a
+        s, c = np.sin(th), np.cos(th)
+        Sigma = r**2 + a**2 * c**2
+        Delta = r**2 - 2 * M * r + a**2
+        A = (r**2 + a**2)**2 - a**2 * Delta * s**2
+        g = dict(tt=-A / (Sigma * Delta), tphi=-2 * M * a * r / (Sigma * Delta), rr=Delta / Sigma,
+                 thth=1.0 / Sigma, phiphi=(Delta - a**2 * s**2) / (Sigma * Delta * s**2))
+        return g, (s, c, Sigma, Delta, A)
 
     def geodesic_equations(self, lambda_, state):
-        raise NotImplementedError
+        """Hamilton's equations on the 8-D state (metrics.py:946-1029): x' = g^{mu nu} p_nu,
+        p' = -(1/2) d g^{ab}/dx p_a p_b, with t and phi cyclic."""
+        t, r, th, phi, p_t, p_r, p_th, p_phi = state
+        M, a = self.M, self.a
+        if r <= self.r_plus * 1.001:
+            return [0.0] * 8
+        g, (s, c, Sigma, Delta, A) = self._inverse_metric(r, th)
+        SD = Sigma * Delta
+        dS_r, dD_r = 2 * r, 2 * r - 2 * M
+        dA_r = 4 * r * (r**2 + a**2) - a**2 * dD_r * s**2
+        dSD_r = dS_r * Delta + Sigma * dD_r
+        d_r = dict(tt=-(dA_r * SD - A * dSD_r) / SD**2,
+                   tphi=-(2 * M * a * (SD - r * dSD_r)) / SD**2,
+                   rr=(dD_r * Sigma - Delta * dS_r) / Sigma**2,
+                   thth=-dS_r / Sigma**2,
+                   phiphi=(dD_r * SD * s**2 - (Delta - a**2 * s**2) * dSD_r * s**2) / (SD * s**2)**2)
+        dS_th = -2 * a**2 * s * c
+        dA_th = -a**2 * Delta * 2 * s * c
+        num, den = Delta - a**2 * s**2, SD * s**2
+        dnum, dden = -a**2 * 2 * s * c, dS_th * Delta * s**2 + SD * 2 * s * c
+        d_th = dict(tt=-(dA_th * SD - A * dS_th * Delta) / SD**2,
+                    tphi=2 * M * a * r * dS_th / (Sigma**2 * Delta),
+                    rr=-Delta * dS_th / Sigma**2,
+                    thth=-dS_th / Sigma**2,
+                    phiphi=(dnum * den - num * dden) / den**2)
+
+        def contract(d):
+            return -0.5 * (d["tt"] * p_t**2 + 2 * d["tphi"] * p_t * p_phi + d["rr"] * p_r**2
+                           + d["thth"] * p_th**2 + d["phiphi"] * p_phi**2)
+        return [g["tt"] * p_t + g["tphi"] * p_phi, g["rr"] * p_r, g["thth"] * p_th,
+                g["tphi"] * p_t + g["phiphi"] * p_phi, 0.0, contract(d_r), contract(d_th), 0.0]
 
     def initial_conditions(self, r_obs, alpha, theta=0.0, theta_obs=np.pi / 2):
-        raise NotImplementedError
+        """Photon at the observer (metrics.py:1033-1109): ``theta`` is the azimuthal screen angle
+        (0 = up, pi/2 = right), ``theta_obs`` the observer's inclination; Bardeen's celestial
+        coordinates give (L, Q), the null condition gives p_r (inward)."""
+        a = self.a
+        g, (s, c, Sigma, Delta, A) = self._inverse_metric(r_obs, theta_obs)
+        E = 1.0
+        rho = r_obs * np.sin(alpha) * np.sqrt(Sigma) / np.sqrt(Delta)
+        alpha_screen, beta_screen = -rho * np.sin(theta), -rho * np.cos(theta)
+        L = -alpha_screen * s * E
+        Q = (beta_screen**2 + c**2 * (alpha_screen**2 - a**2)) * E**2
+        p_t, p_phi = -E, L
+        Theta = max(Q - c**2 * (L**2 / s**2 - a**2 * E**2), 0.0)
+        p_theta = (-1.0 if np.cos(theta) > 0 else 1.0) * np.sqrt(Theta)
+        other = (g["tt"] * p_t**2 + 2 * g["tphi"] * p_t * p_phi + g["thth"] * p_theta**2
+                 + g["phiphi"] * p_phi**2)
+        p_r = -np.sqrt(max(-other / g["rr"], 0.0))
+        return [0.0, r_obs, theta_obs, 0.0, p_t, p_r, p_theta, p_phi]
+
+    # -- ray tracing on the GPU ---------------------------------------------------------
+    def _lambda_max(self, r_obs):
+        return max(5000.0, 6.0 * r_obs)                                   # metrics.py:1120, :1131
 
     def trace_ray(self, r_obs, alpha, theta=0.0, theta_obs=np.pi / 2, phi_max=50.0,
                   axis_refine=False):
-        raise NotImplementedError
+        """-> (final_alpha, n_half_orbits, outcome) (metrics.py:1113-1126); ``phi_max`` is
+        accepted and unused, as in the reference."""
+        t = dev.torch()
+        d = dev.device()
+        fa = t.empty(1, dtype=t.float64, device=d)
+        w = t.empty(1, dtype=t.int64, device=d)
+        st = t.empty(1, dtype=t.int8, device=d)
+        _lib.ext().kerr_trace_batch(t.tensor([float(alpha)], dtype=t.float64, device=d),
+                                    t.tensor([float(theta)], dtype=t.float64, device=d),
+                                    t.tensor([1 if axis_refine else 0], dtype=t.uint8, device=d),
+                                    float(self.M), float(self.a), float(self.r_plus), float(r_obs),
+                                    float(theta_obs), self._lambda_max(r_obs), fa, w, st, None)
+        status = int(st.item())
+        if status == 0:
+            return np.nan, 0, 'invalid'
+        if status == -1:
+            return np.nan, int(w.item()), 'captured'
+        return float(fa.item()), int(w.item()), 'escaped'
 
-    def alpha_crit(self, r_obs, theta_obs=np.pi / 2):
-        raise NotImplementedError
+    def trace_rays_batch(self, r_obs, alphas, thetas, theta_obs, axis_refines, out_fa, out_w, *,
+                         status=None, steps=None):
+        """In-place batch trace (metrics.py:1128-1132): ``out_fa[i]`` = final_alpha or NaN,
+        ``out_w[i]`` = n_half_orbits.  numpy arrays are staged through pinned memory and
+        written back in place; CUDA tensors (float64 / float64 / uint8 or bool / float64 / int64)
+        are used where they are."""
+        t = dev.torch()
+        e = _lib.ext()
+        args = (float(self.M), float(self.a), float(self.r_plus), float(r_obs), float(theta_obs),
+                self._lambda_max(r_obs))
+        if _is_tensor(alphas):
+            ref = None if axis_refines is None else axis_refines.to(t.uint8)
+            e.kerr_trace_batch(alphas, thetas, ref, *args, out_fa, out_w, status, steps)
+            return
+        a_np = np.ascontiguousarray(alphas, dtype=np.float64).reshape(-1)
+        n = a_np.size
+        if n == 0:
+            return
+        d_a = dev.h2d(a_np, "kerr_alpha")
+        d_t = dev.h2d(np.ascontiguousarray(thetas, dtype=np.float64).reshape(-1), "kerr_theta")
+        d_r = None if axis_refines is None else \
+            dev.h2d(np.ascontiguousarray(axis_refines).astype(np.uint8).reshape(-1), "kerr_refine")
+        d_fa = t.empty(n, dtype=t.float64, device=d_a.device)
+        d_w = t.empty(n, dtype=t.int64, device=d_a.device)
+        d_st = t.empty(n, dtype=t.int8, device=d_a.device) if status is not None else None
+        d_steps = t.empty((n, 2), dtype=t.int32, device=d_a.device) if steps is not None else None
+        e.kerr_trace_batch(d_a, d_t, d_r, *args, d_fa, d_w, d_st, d_steps)
+        dev.d2h_into(d_fa, out_fa, "fa")
+        dev.d2h_into(d_w, out_w, "w")
+        if status is not None:
+            dev.d2h_into(d_st, status, "st")
+        if steps is not None:
+            dev.d2h_into(d_steps, steps, "steps")
 
-    def capture_radius(self):
-        raise NotImplementedError
+    def trace_alpha_table_2d(self, alpha32, camera, r_obs, theta_obs, *, row0=0, refine_cols=None,
+                             status=None, steps=None):
+        """Device-resident tracing stage of precompute_final_alpha_lookup_2d: float32 alpha tile
+        [rows, W] (CUDA) -> (final_alpha float32, winding uint16) CUDA tensors, the per-pixel
+        screen angle evaluated on the device.  ``camera`` as _device.camera_vector()."""
+        t = dev.torch()
+        rows = int(alpha32.shape[0])
+        fa = t.empty(alpha32.shape, dtype=t.float32, device=alpha32.device)
+        w = t.empty(alpha32.shape, dtype=t.uint16, device=alpha32.device)
+        _lib.ext().kerr_trace_alpha32(alpha32.contiguous(), camera, int(row0), rows, refine_cols,
+                                      float(self.M), float(self.a), float(self.r_plus), float(r_obs),
+                                      float(theta_obs), self._lambda_max(r_obs), fa, w, status, steps)
+        return fa, w

@@ -36,7 +36,7 @@ WINDING_MAX = 65535  # image_lens.py:12-13 (uint16)
 
 def build(force=False):
     """Compile the C restatement (gcc only; a few hundred ms)."""
-    srcs = [os.path.join(_HERE, f) for f in ("lp_oracle.c", "lp_oracle_rk45.c", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("lp_oracle.c", "lp_oracle_rk45.c", "lp_oracle_kerr.c", "Makefile")]
     if (not force and os.path.exists(_SO)
             and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs)):
         return _SO
@@ -69,6 +69,10 @@ def lib():
         L.lp_oracle_rk45_integrate.argtypes = [d, d, vp, d, d, d, d, d, d, vp, i32, vp, vp, vp, vp, vp]
         L.lp_oracle_rk45_trace_batch.restype = None
         L.lp_oracle_rk45_trace_batch.argtypes = [d, d, vp, i64, d, d, d, d, d, d, vp, vp, vp, vp, vp]
+        L.lp_oracle_kerr_trace_ray.restype = ctypes.c_int
+        L.lp_oracle_kerr_trace_ray.argtypes = [d, d, d, d, d, d, d, d, ctypes.c_int, vp, vp, vp]
+        L.lp_oracle_kerr_trace_batch.restype = None
+        L.lp_oracle_kerr_trace_batch.argtypes = [d, d, d, d, vp, vp, d, d, vp, i64, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -188,6 +192,34 @@ def rk45_trace_batch(M, r_obs, alphas, lambda_max=1000.0, rtol=1e-8, atol=1e-10,
     lib().lp_oracle_rk45_trace_batch(M, r_obs, _p(alphas), n, lambda_max, rtol, atol, max_step,
                                      r_stop_inner, r_stop_outer, _p(state), _p(lam), _p(oc), _p(ns), _p(st))
     return state, lam, oc, ns, st
+
+
+# --------------------------------------------------------------------------
+# Kerr (metrics.py:148-567, :671-679, :840-1132), C
+# --------------------------------------------------------------------------
+def kerr_r_plus(M, a):
+    return M + np.sqrt(M**2 - a**2)                       # metrics.py:852
+
+
+def kerr_lambda_max(r_obs):
+    return max(5000.0, 6.0 * r_obs)                       # metrics.py:1120, :1131
+
+
+def kerr_trace_rays_batch(M, a, r_obs, alphas, thetas, theta_obs, axis_refines=None, lambda_max=None):
+    """Kerr.trace_rays_batch (metrics.py:1128-1132) -> (out_fa f64[n], out_w i64[n], status i8[n],
+    steps i32[n, 2] = (accepted, attempts))."""
+    alphas = np.ascontiguousarray(alphas, dtype=np.float64)
+    thetas = np.ascontiguousarray(thetas, dtype=np.float64)
+    n = alphas.size
+    ar = None if axis_refines is None else np.ascontiguousarray(axis_refines, dtype=np.uint8)
+    fa = np.empty(n, np.float64)
+    w = np.empty(n, np.int64)
+    st = np.empty(n, np.int8)
+    steps = np.empty((n, 2), np.int32)
+    lam = kerr_lambda_max(r_obs) if lambda_max is None else lambda_max
+    lib().lp_oracle_kerr_trace_batch(M, a, float(kerr_r_plus(M, a)), r_obs, _p(alphas), _p(thetas), theta_obs, lam,
+                                     _p(ar), n, _p(fa), _p(w), _p(st), _p(steps))
+    return fa, w, st, steps
 
 
 def precompute_final_alpha_lookup(alpha_lookup, M, r_obs, want_status=False):

@@ -120,3 +120,17 @@ def test_rk45_batch_matches_single(oracle):
         assert np.array_equal(state[i], r["y_final"]) and lam[i] == r["t_final"] and oc[i] == r["outcome"]
         assert tuple(ns[i]) == (r["n_points"], r["nfev"]) and st[i] == r["status"]
     assert oc[-1] == 0 and np.isnan(state[-1]).all() and st[-1] == -2
+
+
+def test_kerr_golden_rays(oracle, golden):
+    """The Kerr restatement (oracle/lp_oracle_kerr.c: DP45 on the reduced 5-D state) against the
+    reference's Kerr.trace_rays_batch — bit for bit (final_alpha, winding, status) for 16 525
+    rays over five (M, a, r_obs, theta_obs) configurations, axis_refine on and off."""
+    g = golden("kerr_rays.npz")
+    for k, row in enumerate(g["cfg"]):
+        M, a, r_obs, th_obs = (float(x) for x in row[:4])
+        p = "c%d_" % k
+        fa, w, st, _ = oracle.kerr_trace_rays_batch(M, a, r_obs, g[p + "alpha"], g[p + "theta"], th_obs, g[p + "refine"])
+        assert bits_equal(fa, g[p + "fa"]), k
+        assert np.array_equal(w, g[p + "w"]) and np.array_equal(st, g[p + "status"]), k
+        assert abs(oracle.kerr_r_plus(M, a) - row[5]) == 0.0
