@@ -1,5 +1,6 @@
 """light_path_tracer_b200 — B200-native (sm_100a) implementation of the per-pixel
-Schwarzschild null-geodesic ray-tracing path of dhg14n9/Light-path-tracer.
+null-geodesic ray-tracing path of dhg14n9/Light-path-tracer (Schwarzschild: Binet RK4 fast path
+and the generic RK45 integrator; Kerr: the reference's Dormand-Prince tracer).
 
 The sub-modules mirror the reference's flat modules and keep their call signatures:
 
