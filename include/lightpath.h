@@ -274,6 +274,18 @@ int lp_schw_rk45_integrate_paths(const double *state0, int64_t n,
                                  int8_t *out_outcome, int32_t *out_nsteps, int8_t *out_status,
                                  void *stream);
 
+/* integrate_geodesic for a Kerr metric (Kerr.geodesic_equations, metrics.py:946-1029): same
+ * stepper, events and outputs as lp_schw_rk45_integrate_paths.  r_stop_inner <= 0 selects
+ * capture_radius() = 1.01 r_plus (metrics.py:861-862). */
+int lp_kerr_rk45_integrate_paths(const double *state0, int64_t n,
+                                 double M, double a, double r_plus,
+                                 double lambda_max, double rtol, double atol, double max_step,
+                                 double r_stop_inner, double r_stop_outer,
+                                 double *traj, int32_t max_points, int32_t *n_points,
+                                 double *out_state, double *out_lambda,
+                                 int8_t *out_outcome, int32_t *out_nsteps, int8_t *out_status,
+                                 void *stream);
+
 /* ---- Kerr tracer (next row after the Schwarzschild path) ------ */
 
 /* Replaces Kerr.trace_rays_batch / _trace_rays_batch_kerr (metrics.py:1128-1132,

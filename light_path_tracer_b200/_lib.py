@@ -66,6 +66,8 @@ SYMBOLS = {
                                                 _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "lp_schw_rk45_integrate_paths": (ctypes.c_int, [_VP, _I64, _D, _D, _D, _D, _D, _D, _D, _D, _VP, _I32,
                                                     _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "lp_kerr_rk45_integrate_paths": (ctypes.c_int, [_VP, _I64, _D, _D, _D, _D, _D, _D, _D, _D, _D, _VP, _I32,
+                                                    _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "lp_kerr_trace_batch_f64": (ctypes.c_int, [_VP, _VP, _VP, _I64, _D, _D, _D, _D, _D, _D, _VP, _VP, _VP, _VP, _VP]),
     "lp_kerr_trace_alpha32": (ctypes.c_int, [_VP, _CAMP, _I32, _I32, _VP, _D, _D, _D, _D, _D, _D, _VP, _VP, _VP,
                                              _VP, _VP]),

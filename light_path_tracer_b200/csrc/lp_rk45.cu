@@ -62,6 +62,7 @@ struct Rk45Args {
     const double *state0;       // ... or explicit initial states [n][8] (integrate_geodesic's state0)
     long long n;
     double R_S, r_obs, lambda_max, rtol, atol, max_step;
+    double kerr_M, kerr_a, r_floor;   // METRIC 1; r_floor = 1.001 R_S (metrics.py:766) or 1.001 r_plus (:950)
     double r_in, r_out;         // r_out <= 0: 2 * state0[1] (geodesic_tracer.py:44-45)
     double sqrt_f0, f0;         // metrics.py:797 / :757-759, hoisted
     double *out_state;          // [n][8]
@@ -125,6 +126,52 @@ __device__ __forceinline__ void rk_rhs(double R_S, double r_floor, double p_t, d
     d[5] = tc.c * pp2 * ir2 * is2 * is1;
 #endif
 }
+
+// Kerr.geodesic_equations (metrics.py:946-1029) for the moving components (same six: p_t and
+// p_phi are cyclic), over three shared reciprocals like the Schwarzschild form above.  The
+// generic path has no sin^2(theta) floor (metrics.py:953-959), unlike the numba tracer.
+__device__ __forceinline__ void rk_rhs_kerr(double M, double a, double r_floor, double p_t, double p_phi,
+                                            const double (&y)[RK_NC], ThetaCache &tc, double (&d)[RK_NC])
+{
+    const double r = y[1], th = y[2], p_r = y[4], p_th = y[5];
+    if (r <= r_floor) {                                   // metrics.py:950-951
+#pragma unroll
+        for (int i = 0; i < RK_NC; ++i) d[i] = 0.0;
+        return;
+    }
+    if (th != tc.th) { sincos(th, &tc.s, &tc.c); tc.th = th; }
+    const double sn = tc.s, cs = tc.c, s2 = sn * sn, a2 = a * a, r2 = r * r;
+    const double Sigma = r2 + a2 * (cs * cs);
+    const double Delta = r2 - 2.0 * M * r + a2;
+    const double A = (r2 + a2) * (r2 + a2) - a2 * Delta * s2;
+    const double iS = fast_rcp(Sigma), iD = fast_rcp(Delta), is2 = fast_rcp(s2);
+    const double iSD = iS * iD, iS2 = iS * iS, iSD2 = iSD * iSD, iden2 = iSD2 * (is2 * is2);
+    const double twoMa = 2.0 * M * a, SD = Sigma * Delta;
+    const double num = Delta - a2 * s2, den = SD * s2;
+    const double g_tt = -A * iSD, g_tphi = -twoMa * r * iSD, g_phiphi = num * iSD * is2;
+    d[0] = g_tt * p_t + g_tphi * p_phi;
+    d[1] = Delta * iS * p_r;
+    d[2] = iS * p_th;
+    d[3] = g_tphi * p_t + g_phiphi * p_phi;
+    const double dS_r = 2.0 * r, dD_r = 2.0 * r - 2.0 * M;
+    const double dA_r = 4.0 * r * (r2 + a2) - a2 * dD_r * s2;
+    const double X = dS_r * Delta + Sigma * dD_r;
+    const double pt2 = p_t * p_t, ptpp = p_t * p_phi, pr2 = p_r * p_r, pth2 = p_th * p_th, pp2 = p_phi * p_phi;
+    d[4] = -0.5 * (-(dA_r * SD - A * X) * iSD2 * pt2 + 2.0 * (-(twoMa * (SD - r * X)) * iSD2) * ptpp
+                   + (dD_r * Sigma - Delta * dS_r) * iS2 * pr2 + (-dS_r * iS2) * pth2
+                   + (dD_r * den - num * X * s2) * iden2 * pp2);
+    const double sc2 = 2.0 * sn * cs;
+    const double dS_th = -a2 * sc2, dA_th = -a2 * Delta * sc2;
+    const double dden_th = dS_th * Delta * s2 + SD * sc2;
+    d[5] = -0.5 * (-(dA_th * SD - A * dS_th * Delta) * iSD2 * pt2 + 2.0 * (twoMa * r * dS_th * iS2 * iD) * ptpp
+                   + (-Delta * dS_th * iS2) * pr2 + (-dS_th * iS2) * pth2
+                   + (-a2 * sc2 * den - num * dden_th) * iden2 * pp2);
+}
+
+// METRIC 0: Schwarzschild (R_S), 1: Kerr (M, a)
+template <int METRIC>
+__device__ __forceinline__ void rk_f(const struct Rk45Args &a, double r_floor, double p_t, double p_phi,
+                                     const double (&y)[RK_NC], ThetaCache &tc, double (&d)[RK_NC]);
 
 // Quartic dense output of one component (rk.py:723-737), sequential like the oracle.
 __device__ __forceinline__ double dense_comp(const double (&q)[4], double h, double y_old, double x)
@@ -195,7 +242,20 @@ __device__ __forceinline__ void write_point(const Rk45Args &a, long long idx, in
     row[5] = p_t; row[6] = y[4]; row[7] = y[5]; row[8] = p_phi;
 }
 
-template <int MINB>
+template <>
+__device__ __forceinline__ void rk_f<0>(const Rk45Args &a, double r_floor, double p_t, double p_phi,
+                                        const double (&y)[RK_NC], ThetaCache &tc, double (&d)[RK_NC])
+{
+    rk_rhs(a.R_S, r_floor, p_t, p_phi, y, tc, d);
+}
+template <>
+__device__ __forceinline__ void rk_f<1>(const Rk45Args &a, double r_floor, double p_t, double p_phi,
+                                        const double (&y)[RK_NC], ThetaCache &tc, double (&d)[RK_NC])
+{
+    rk_rhs_kerr(a.kerr_M, a.kerr_a, r_floor, p_t, p_phi, y, tc, d);
+}
+
+template <int MINB, int METRIC>
 __global__ void __launch_bounds__(RK_BLOCK, MINB)
 lp_rk45_kernel(const Rk45Args a)
 {
@@ -203,7 +263,7 @@ lp_rk45_kernel(const Rk45Args a)
     const int lane = threadIdx.x & 31;
     const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const double R_S = a.R_S, r_floor = R_S * 1.001, rtol = a.rtol, atol = a.atol;
+    const double r_floor = a.r_floor, rtol = a.rtol, atol = a.atol;
     const double t_bound = a.lambda_max, max_step = a.max_step;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
 
@@ -261,7 +321,7 @@ lp_rk45_kernel(const Rk45Args a)
                 } else {
                     t = 0.0;
                     r_out = a.r_out > 0.0 ? a.r_out : y[1] * 2.0;
-                    rk_rhs(R_S, r_floor, p_t, p_phi, y, tc, f);                 // rk.py:95
+                    rk_f<METRIC>(a, r_floor, p_t, p_phi, y, tc, f);               // rk.py:95
                     // ---- select_initial_step, common.py:68-134 (direction = +1) ----
                     const double interval = fabs(t_bound - t);
                     double sc[RK_NC], d0s = 0.0, d1s = 0.0;
@@ -281,7 +341,7 @@ lp_rk45_kernel(const Rk45Args a)
                     double y1[RK_NC], f1[RK_NC], d2s = 0.0;
 #pragma unroll
                     for (int i = 0; i < RK_NC; ++i) y1[i] = y[i] + h0 * f[i];
-                    rk_rhs(R_S, r_floor, p_t, p_phi, y1, tc, f1);
+                    rk_f<METRIC>(a, r_floor, p_t, p_phi, y1, tc, f1);
 #pragma unroll
                     for (int i = 0; i < RK_NC; ++i) { const double v2 = (f1[i] - f[i]) / sc[i]; d2s = fma(v2, v2, d2s); }
                     const double d2 = rms8(d2s) / h0;
@@ -348,7 +408,7 @@ lp_rk45_kernel(const Rk45Args a)
                     for (int j = 1; j < s; ++j) dy = fma(K[j][i], c_A[s][j], dy);
                     ys[i] = fma(dy, h, y[i]);
                 }
-                rk_rhs(R_S, r_floor, p_t, p_phi, ys, tc, K[s]);
+                rk_f<METRIC>(a, r_floor, p_t, p_phi, ys, tc, K[s]);
             }
             double y_new[RK_NC];
 #pragma unroll
@@ -360,7 +420,7 @@ lp_rk45_kernel(const Rk45Args a)
                 acc = fma(K[5][i], c_B[5], acc);
                 y_new[i] = fma(h, acc, y[i]);
             }
-            rk_rhs(R_S, r_floor, p_t, p_phi, y_new, tc, K[6]);
+            rk_f<METRIC>(a, r_floor, p_t, p_phi, y_new, tc, K[6]);
             // ---- error norm, rk.py:105-109, :148-149 ----
             double esum = 0.0;
 #pragma unroll
@@ -449,7 +509,8 @@ lp_rk45_kernel(const Rk45Args a)
     }
 }
 
-static int rk45_launch(const double *alphas, const double *state0, int64_t n, double M, double R_S, double r_obs,
+static int rk45_launch(bool metric_is_kerr, double kerr_a, const double *alphas, const double *state0, int64_t n,
+                       double M, double R_S, double r_obs,
                        double lambda_max, double rtol, double atol, double max_step,
                        double r_stop_inner, double r_stop_outer,
                        double *out_state, double *out_lambda, int8_t *out_outcome,
@@ -464,6 +525,9 @@ static int rk45_launch(const double *alphas, const double *state0, int64_t n, do
     Rk45Args a;
     a.alphas = alphas; a.state0 = state0; a.n = n;
     a.R_S = R_S; a.r_obs = r_obs; a.lambda_max = lambda_max;
+    a.kerr_M = M; a.kerr_a = kerr_a;
+    // R_S carries r_plus for Kerr: capture_radius() = 1.01 r_plus (metrics.py:861-862)
+    a.r_floor = R_S * 1.001;
     a.rtol = rtol < 100 * 2.220446049250313e-16 ? 100 * 2.220446049250313e-16 : rtol;   // common.py validate_tol
     a.atol = atol; a.max_step = max_step;
     a.r_in = r_stop_inner > 0.0 ? r_stop_inner : R_S * 1.01;                           // metrics.py:750-751
@@ -481,16 +545,19 @@ static int rk45_launch(const double *alphas, const double *state0, int64_t n, do
         const int v = e ? atoi(e) : 0;
         minb = (v == 2 || v == 3 || v == 4) ? v : RK_DEFAULT_MINB;
     }
-    const void *fn = minb == 2 ? (const void *)lp_rk45_kernel<2>
-                   : minb == 3 ? (const void *)lp_rk45_kernel<3> : (const void *)lp_rk45_kernel<4>;
+    const bool kerr = metric_is_kerr;
+    const void *fn = kerr ? (const void *)lp_rk45_kernel<2, 1>
+                   : minb == 2 ? (const void *)lp_rk45_kernel<2, 0>
+                   : minb == 3 ? (const void *)lp_rk45_kernel<3, 0> : (const void *)lp_rk45_kernel<4, 0>;
     int grid = 0;
     int rc = lp_grid_for(fn, RK_BLOCK, &grid);
     if (rc != LP_OK) return rc;
     const long long chunks = (n + RK_BLOCK - 1) / RK_BLOCK;
     if (chunks < grid) grid = (int)chunks;
-    if (minb == 2) lp_rk45_kernel<2><<<grid, RK_BLOCK, 0, stream>>>(a);
-    else if (minb == 3) lp_rk45_kernel<3><<<grid, RK_BLOCK, 0, stream>>>(a);
-    else lp_rk45_kernel<4><<<grid, RK_BLOCK, 0, stream>>>(a);
+    if (kerr) lp_rk45_kernel<2, 1><<<grid, RK_BLOCK, 0, stream>>>(a);
+    else if (minb == 2) lp_rk45_kernel<2, 0><<<grid, RK_BLOCK, 0, stream>>>(a);
+    else if (minb == 3) lp_rk45_kernel<3, 0><<<grid, RK_BLOCK, 0, stream>>>(a);
+    else lp_rk45_kernel<4, 0><<<grid, RK_BLOCK, 0, stream>>>(a);
     return lp_check_launch();
 }
 
@@ -502,7 +569,7 @@ extern "C" int lp_schw_rk45_trace_batch(const double *alphas, int64_t n,
                                         int8_t *out_outcome, int32_t *out_nsteps, int8_t *out_status,
                                         void *stream)
 {
-    return rk45_launch(alphas, nullptr, n, M, R_S, r_obs, lambda_max, rtol, atol, max_step, r_stop_inner,
+    return rk45_launch(false, 0.0, alphas, nullptr, n, M, R_S, r_obs, lambda_max, rtol, atol, max_step, r_stop_inner,
                        r_stop_outer, out_state, out_lambda, out_outcome, out_nsteps, out_status,
                        nullptr, 0, nullptr, (cudaStream_t)stream);
 }
@@ -517,7 +584,7 @@ extern "C" int lp_schw_rk45_trace_paths(const double *alphas, int64_t n,
                                         void *stream)
 {
     if (n > 0 && (!traj || !n_points || max_points < 1)) return LP_ERR_INVALID_ARG;
-    return rk45_launch(alphas, nullptr, n, M, R_S, r_obs, lambda_max, rtol, atol, max_step, r_stop_inner,
+    return rk45_launch(false, 0.0, alphas, nullptr, n, M, R_S, r_obs, lambda_max, rtol, atol, max_step, r_stop_inner,
                        r_stop_outer, out_state, out_lambda, out_outcome, out_nsteps, out_status,
                        traj, max_points, n_points, (cudaStream_t)stream);
 }
@@ -533,7 +600,24 @@ extern "C" int lp_schw_rk45_integrate_paths(const double *state0, int64_t n,
 {
     if (n > 0 && traj && (!n_points || max_points < 1)) return LP_ERR_INVALID_ARG;
     // r_obs only feeds initial_conditions, which explicit states bypass
-    return rk45_launch(nullptr, state0, n, M, R_S, 4.0 * R_S, lambda_max, rtol, atol, max_step, r_stop_inner,
+    return rk45_launch(false, 0.0, nullptr, state0, n, M, R_S, 4.0 * R_S, lambda_max, rtol, atol, max_step, r_stop_inner,
                        r_stop_outer, out_state, out_lambda, out_outcome, out_nsteps, out_status,
+                       traj, max_points, n_points, (cudaStream_t)stream);
+}
+
+// The same for a Kerr metric (Kerr.geodesic_equations, metrics.py:946-1029): explicit initial
+// states only (Kerr.initial_conditions is host arithmetic).  r_plus = M + sqrt(M^2 - a^2).
+extern "C" int lp_kerr_rk45_integrate_paths(const double *state0, int64_t n,
+                                            double M, double a, double r_plus,
+                                            double lambda_max, double rtol, double atol, double max_step,
+                                            double r_stop_inner, double r_stop_outer,
+                                            double *traj, int32_t max_points, int32_t *n_points,
+                                            double *out_state, double *out_lambda,
+                                            int8_t *out_outcome, int32_t *out_nsteps, int8_t *out_status,
+                                            void *stream)
+{
+    if (n > 0 && traj && (!n_points || max_points < 1)) return LP_ERR_INVALID_ARG;
+    return rk45_launch(true, a, nullptr, state0, n, M, r_plus, 4.0 * r_plus, lambda_max, rtol, atol, max_step,
+                       r_stop_inner, r_stop_outer, out_state, out_lambda, out_outcome, out_nsteps, out_status,
                        traj, max_points, n_points, (cudaStream_t)stream);
 }

@@ -250,6 +250,27 @@ void rk45_integrate_paths(const Tensor &state0, double M, double R_S, double lam
           "lp_schw_rk45_integrate_paths");
 }
 
+void kerr_rk45_integrate_paths(const Tensor &state0, double M, double a, double r_plus, double lambda_max, double rtol,
+                               double atol, double max_step, double r_in, double r_out, OptTensor traj,
+                               int64_t max_points, OptTensor n_points, Tensor out_state, Tensor out_lambda,
+                               Tensor out_outcome, Tensor out_nsteps, Tensor out_status)
+{
+    const int64_t n = state0.numel() / 8;
+    c10::cuda::CUDAGuard g(state0.device());
+    check(lp_kerr_rk45_integrate_paths((const double *)ptr(state0, c10::ScalarType::Double, "state0", 0), n, M, a, r_plus,
+                                       lambda_max, rtol, atol, max_step, r_in, r_out,
+                                       (double *)optptr(traj, c10::ScalarType::Double, "traj", n * max_points * 9),
+                                       (int32_t)max_points,
+                                       (int32_t *)optptr(n_points, c10::ScalarType::Int, "n_points", n),
+                                       (double *)ptr(out_state, c10::ScalarType::Double, "out_state", 8 * n),
+                                       (double *)ptr(out_lambda, c10::ScalarType::Double, "out_lambda", n),
+                                       (int8_t *)ptr(out_outcome, c10::ScalarType::Char, "out_outcome", n),
+                                       (int32_t *)ptr(out_nsteps, c10::ScalarType::Int, "out_nsteps", 2 * n),
+                                       (int8_t *)ptr(out_status, c10::ScalarType::Char, "out_status", n),
+                                       stream_of(state0)),
+          "lp_kerr_rk45_integrate_paths");
+}
+
 void kerr_trace_batch(const Tensor &alphas, const Tensor &thetas, OptTensor refine, double M, double a, double r_plus,
                       double r_obs, double theta_obs, double lambda_max, Tensor out_fa, Tensor out_w,
                       OptTensor status, OptTensor steps)
@@ -325,6 +346,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.def("rk45_trace_batch", &rk45_trace_batch);
     m.def("rk45_trace_paths", &rk45_trace_paths);
     m.def("rk45_integrate_paths", &rk45_integrate_paths);
+    m.def("kerr_rk45_integrate_paths", &kerr_rk45_integrate_paths);
     m.def("kerr_trace_batch", &kerr_trace_batch);
     m.def("kerr_trace_alpha32", &kerr_trace_alpha32);
     m.def("bench_dfma", &bench_dfma);

@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _device as dev
 from . import _lib
-from .metrics import Schwarzschild
+from .metrics import Schwarzschild, Kerr
 
 # solve_ivp arguments hard-coded by the reference (geodesic_tracer.py:57-67)
 RTOL, ATOL, MAX_STEP = 1e-8, 1e-10, 1.0
@@ -41,8 +41,15 @@ class OdeResult(dict):
 def _require_schwarzschild(metric):
     if not isinstance(metric, Schwarzschild):
         raise NotImplementedError(
-            "the CUDA generic integrator carries the Schwarzschild right-hand side "
-            "(metrics.py:763-790); %s is not supported" % type(metric).__name__)
+            "this entry point evaluates Schwarzschild.initial_conditions on the device "
+            "(metrics.py:794-809); %s is not supported" % type(metric).__name__)
+
+
+def _require_known_metric(metric):
+    if not isinstance(metric, (Schwarzschild, Kerr)):
+        raise NotImplementedError(
+            "the CUDA generic integrator carries the Schwarzschild and Kerr right-hand sides "
+            "(metrics.py:763-790, :946-1029); %s is not supported" % type(metric).__name__)
 
 
 def _alloc(t, n, device):
@@ -57,7 +64,10 @@ def _paths(metric, alphas=None, state0=None, r_obs=None, lambda_max=1000.0, r_st
     more accepted points than expected.  Returns host arrays."""
     t = dev.torch()
     e = _lib.ext()
-    _require_schwarzschild(metric)
+    if state0 is None:
+        _require_schwarzschild(metric)
+    else:
+        _require_known_metric(metric)
     r_in = float(metric.capture_radius() if r_stop_inner is None else r_stop_inner)
     r_out = float(0.0 if r_stop_outer is None else r_stop_outer)
     if r_stop_outer is not None and not r_out > 0.0:
@@ -74,6 +84,10 @@ def _paths(metric, alphas=None, state0=None, r_obs=None, lambda_max=1000.0, r_st
             e.rk45_trace_paths(d_in, float(metric.M), float(metric.R_S), float(r_obs), float(lambda_max),
                                RTOL, ATOL, MAX_STEP, r_in, r_out, traj, cap, npts, state, lam, outcome,
                                nsteps, status)
+        elif isinstance(metric, Kerr):
+            e.kerr_rk45_integrate_paths(d_in, float(metric.M), float(metric.a), float(metric.r_plus),
+                                        float(lambda_max), RTOL, ATOL, MAX_STEP, r_in, r_out, traj, cap, npts,
+                                        state, lam, outcome, nsteps, status)
         else:
             e.rk45_integrate_paths(d_in, float(metric.M), float(metric.R_S), float(lambda_max), RTOL, ATOL,
                                    MAX_STEP, r_in, r_out, traj, cap, npts, state, lam, outcome, nsteps, status)
@@ -125,6 +139,20 @@ def trace_paths(metric, r_obs, alphas, lambda_max=1000.0, r_stop_inner=None, r_s
     """``[trace_ray(metric, r_obs, a) for a in alphas]`` in one launch (initial conditions
     evaluated on the device)."""
     alphas = np.atleast_1d(np.asarray(alphas, dtype=np.float64))
+    if not isinstance(metric, Schwarzschild):
+        # any other metric: its own initial_conditions on the host, one launch for the valid rays
+        states = [metric.initial_conditions(r_obs, float(al)) for al in alphas]
+        good = [i for i, s0 in enumerate(states) if s0 is not None]
+        res = [(None, 'invalid')] * alphas.size
+        if good:
+            s0 = np.array([states[i] for i in good], dtype=np.float64)
+            traj, npts, state, lam, outcome, nsteps, status, r_in, r_out = _paths(
+                metric, state0=s0, lambda_max=lambda_max, r_stop_inner=r_stop_inner, r_stop_outer=r_stop_outer)
+            for j, i in enumerate(good):
+                r_out_used = r_out if r_out > 0.0 else float(s0[j, 1]) * 2.0
+                res[i] = (_solution(traj[j], npts[j], state[j], lam[j], nsteps[j], status[j], r_in, r_out_used),
+                          _OUTCOME[int(outcome[j])])
+        return res
     traj, npts, state, lam, outcome, nsteps, status, r_in, r_out = _paths(
         metric, alphas=alphas, r_obs=r_obs, lambda_max=lambda_max, r_stop_inner=r_stop_inner,
         r_stop_outer=r_stop_outer)

@@ -69,6 +69,8 @@ def lib():
         L.lp_oracle_rk45_integrate.argtypes = [d, d, vp, d, d, d, d, d, d, vp, i32, vp, vp, vp, vp, vp]
         L.lp_oracle_rk45_trace_batch.restype = None
         L.lp_oracle_rk45_trace_batch.argtypes = [d, d, vp, i64, d, d, d, d, d, d, vp, vp, vp, vp, vp]
+        L.lp_oracle_rk45_integrate_kerr.restype = ctypes.c_int
+        L.lp_oracle_rk45_integrate_kerr.argtypes = [d, d, d, vp, d, d, d, d, d, d, vp, i32, vp, vp, vp, vp, vp]
         L.lp_oracle_kerr_trace_ray.restype = ctypes.c_int
         L.lp_oracle_kerr_trace_ray.argtypes = [d, d, d, d, d, d, d, d, ctypes.c_int, vp, vp, vp]
         L.lp_oracle_kerr_trace_batch.restype = None
@@ -176,6 +178,25 @@ def rk45_trace_ray(M, r_obs, alpha, lambda_max=1000.0, r_stop_inner=None, r_stop
     return dict(t=traj[:n, 0].copy(), y=traj[:n, 1:].T.copy(), nfev=int(nfev.value),
                 status=int(status.value), outcome=int(oc), n_points=int(npts.value),
                 t_final=tf.value, y_final=yf, state0=s0)
+
+
+def rk45_integrate_kerr(M, a, state0, lambda_max=1000.0, r_stop_inner=None, r_stop_outer=None,
+                        rtol=1e-8, atol=1e-10, max_step=1.0, max_points=8192):
+    """integrate_geodesic(Kerr(M, a), state0, ...) (geodesic_tracer.py:22-71 on metrics.py:946-1029)."""
+    s0 = np.ascontiguousarray(state0, dtype=np.float64).copy()
+    r_plus = float(kerr_r_plus(M, a))
+    r_in = r_plus * 1.01 if r_stop_inner is None else r_stop_inner
+    r_out = s0[1] * 2.0 if r_stop_outer is None else r_stop_outer
+    traj = np.empty((max_points, 9), np.float64)
+    npts, nfev, status = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    tf = ctypes.c_double()
+    yf = np.empty(8, np.float64)
+    oc = lib().lp_oracle_rk45_integrate_kerr(M, a, r_plus, _p(s0), lambda_max, rtol, atol, max_step, r_in, r_out,
+                                             _p(traj), max_points, ctypes.addressof(npts), ctypes.addressof(nfev),
+                                             ctypes.addressof(status), ctypes.addressof(tf), _p(yf))
+    n = min(int(npts.value), max_points)
+    return dict(t=traj[:n, 0].copy(), y=traj[:n, 1:].T.copy(), nfev=int(nfev.value), status=int(status.value),
+                outcome=int(oc), n_points=int(npts.value), t_final=tf.value, y_final=yf, state0=s0)
 
 
 def rk45_trace_batch(M, r_obs, alphas, lambda_max=1000.0, rtol=1e-8, atol=1e-10, max_step=1.0,

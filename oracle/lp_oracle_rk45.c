@@ -56,12 +56,63 @@ static const double P_[7][4] = {
     {0, -282668133.0 / 205662961, 2019193451.0 / 616988883, -1453857185.0 / 822651844},
     {0, 40617522.0 / 29380423, -110615467.0 / 29380423, 69997945.0 / 29380423}};
 
-typedef struct { double M, R_S; int nfev; } rhs_ctx;
+typedef struct { double M, R_S; int nfev; int kerr; double a, r_plus; } rhs_ctx;
+
+/* Kerr.geodesic_equations, metrics.py:946-1029 (the generic path's 8-D form: no sin^2 floor) */
+static void rhs_kerr(rhs_ctx *c, const double *s, double *d)
+{
+    const double r = s[1], th = s[2], p_t = s[4], p_r = s[5], p_th = s[6], p_phi = s[7];
+    const double M = c->M, a = c->a;
+    if (r <= c->r_plus * 1.001) { for (int i = 0; i < N; ++i) d[i] = 0.0; return; }
+    const double sin_th = sin(th), cos_th = cos(th);
+    const double r2 = r * r, a2 = a * a, s2 = sin_th * sin_th;
+    const double Sigma = r2 + a2 * (cos_th * cos_th);
+    const double Delta = r2 - 2 * M * r + a2;
+    const double A = (r2 + a2) * (r2 + a2) - a2 * Delta * s2;
+    const double g_tt_inv = -A / (Sigma * Delta);
+    const double g_tphi_inv = -2 * M * a * r / (Sigma * Delta);
+    const double g_rr_inv = Delta / Sigma;
+    const double g_thth_inv = 1.0 / Sigma;
+    const double g_phiphi_inv = (Delta - a2 * s2) / (Sigma * Delta * s2);
+    d[0] = g_tt_inv * p_t + g_tphi_inv * p_phi;
+    d[1] = g_rr_inv * p_r;
+    d[2] = g_thth_inv * p_th;
+    d[3] = g_tphi_inv * p_t + g_phiphi_inv * p_phi;
+    const double dSigma_dr = 2 * r, dDelta_dr = 2 * r - 2 * M;
+    const double dA_dr = 4 * r * (r2 + a2) - a2 * dDelta_dr * s2;
+    const double SD = Sigma * Delta;
+    const double dg_tt_inv_dr = (-(dA_dr * Sigma * Delta - A * (dSigma_dr * Delta + Sigma * dDelta_dr)) / (SD * SD));
+    const double dg_tphi_inv_dr = (-(2 * M * a * (Sigma * Delta - r * (dSigma_dr * Delta + Sigma * dDelta_dr)))
+                                   / (SD * SD));
+    const double dg_rr_inv_dr = (dDelta_dr * Sigma - Delta * dSigma_dr) / (Sigma * Sigma);
+    const double dg_thth_inv_dr = -dSigma_dr / (Sigma * Sigma);
+    const double den_r = Sigma * Delta * s2;
+    const double dg_phiphi_inv_dr = ((dDelta_dr * Sigma * Delta * s2
+                                      - (Delta - a2 * s2) * (dSigma_dr * Delta + Sigma * dDelta_dr) * s2)
+                                     / (den_r * den_r));
+    d[4] = 0.0;
+    d[5] = -0.5 * (dg_tt_inv_dr * (p_t * p_t) + 2 * dg_tphi_inv_dr * p_t * p_phi + dg_rr_inv_dr * (p_r * p_r)
+                   + dg_thth_inv_dr * (p_th * p_th) + dg_phiphi_inv_dr * (p_phi * p_phi));
+    const double dSigma_dth = -2 * a2 * sin_th * cos_th;
+    const double dA_dth = -a2 * Delta * 2 * sin_th * cos_th;
+    const double dg_tt_inv_dth = (-(dA_dth * Sigma * Delta - A * dSigma_dth * Delta) / (SD * SD));
+    const double dg_tphi_inv_dth = 2 * M * a * r * dSigma_dth / ((Sigma * Sigma) * Delta);
+    const double dg_rr_inv_dth = -Delta * dSigma_dth / (Sigma * Sigma);
+    const double dg_thth_inv_dth = -dSigma_dth / (Sigma * Sigma);
+    const double num = Delta - a2 * s2, den = Sigma * Delta * s2;
+    const double dnum_dth = -a2 * 2 * sin_th * cos_th;
+    const double dden_dth = (dSigma_dth * Delta * s2 + Sigma * Delta * 2 * sin_th * cos_th);
+    const double dg_phiphi_inv_dth = (dnum_dth * den - num * dden_dth) / (den * den);
+    d[6] = -0.5 * (dg_tt_inv_dth * (p_t * p_t) + 2 * dg_tphi_inv_dth * p_t * p_phi + dg_rr_inv_dth * (p_r * p_r)
+                   + dg_thth_inv_dth * (p_th * p_th) + dg_phiphi_inv_dth * (p_phi * p_phi));
+    d[7] = 0.0;
+}
 
 /* Schwarzschild.geodesic_equations, metrics.py:763-790 */
 static void rhs(rhs_ctx *c, const double *s, double *d)
 {
     c->nfev++;
+    if (c->kerr) { rhs_kerr(c, s, d); return; }
     const double r = s[1], th = s[2], p_t = s[4], p_r = s[5], p_th = s[6], p_phi = s[7];
     const double R_S = c->R_S;
     if (r <= R_S * 1.001) { for (int i = 0; i < N; ++i) d[i] = 0.0; return; }
@@ -197,6 +248,11 @@ int lp_oracle_rk45_initial_conditions(double M, double r_obs, double alpha, doub
     return 1;
 }
 
+/* Metric selection for lp_oracle_rk45_integrate: thread-local so that the C signature of the
+ * Schwarzschild path stays as it was (test infrastructure, single caller). */
+static __thread int g_kerr_a_set = 0;
+static __thread double g_kerr_a = 0.0, g_kerr_r_plus = 0.0;
+
 /*
  * integrate_geodesic (geodesic_tracer.py:22-71).
  *   traj: optional [max_points][9] rows (t, y[8]) = OdeResult.t / .y columns; *n_points = the
@@ -210,7 +266,7 @@ int lp_oracle_rk45_integrate(double M, double R_S, const double *state0, double 
                              double *traj, int32_t max_points, int32_t *n_points, int32_t *nfev,
                              int32_t *status_out, double *t_final, double *y_final)
 {
-    rhs_ctx ctx = {M, R_S, 0};
+    rhs_ctx ctx = {M, R_S, 0, g_kerr_a_set, g_kerr_a, g_kerr_r_plus};
     double t = 0.0, y[N], f[N], K[7][N];
     const double t_bound = lambda_max;
     memcpy(y, state0, sizeof y);
@@ -341,4 +397,20 @@ void lp_oracle_rk45_trace_batch(double M, double r_obs, const double *alphas, in
         if (out_nsteps) { out_nsteps[2 * i] = np_; out_nsteps[2 * i + 1] = nf; }
         if (out_status) out_status[i] = (int8_t)st;
     }
+}
+
+/* integrate_geodesic with a Kerr metric (metrics.py:946-1029); r_stop_inner default
+ * capture_radius() = 1.01 r_plus (metrics.py:861-862) is the caller's to pass. */
+int lp_oracle_rk45_integrate_kerr(double M, double a, double r_plus, const double *state0, double lambda_max,
+                                  double rtol, double atol, double max_step,
+                                  double r_stop_inner, double r_stop_outer,
+                                  double *traj, int32_t max_points, int32_t *n_points, int32_t *nfev,
+                                  int32_t *status_out, double *t_final, double *y_final)
+{
+    g_kerr_a_set = 1; g_kerr_a = a; g_kerr_r_plus = r_plus;
+    const int oc = lp_oracle_rk45_integrate(M, 2 * M, state0, lambda_max, rtol, atol, max_step, r_stop_inner,
+                                            r_stop_outer, traj, max_points, n_points, nfev, status_out, t_final,
+                                            y_final);
+    g_kerr_a_set = 0;
+    return oc;
 }

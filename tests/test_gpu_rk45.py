@@ -165,3 +165,31 @@ def test_device_tensor_batch_and_main(native, oracle, capsys):
     main_mod.main()
     out = capsys.readouterr().out
     assert "ESCAPED" in out and "b = 7.1" in out
+
+
+def test_kerr_generic_path_golden(native, golden, oracle):
+    """geodesic_tracer.trace_ray with a Kerr metric (scipy RK45 on Kerr.geodesic_equations,
+    metrics.py:946-1029) against the reference fixture: outcome, accepted points and nfev exact,
+    final state within 1e-9, trajectory within 1e-7."""
+    from light_path_tracer_b200.metrics import Kerr
+    gt = _gt()
+    g = golden("kerr_rk45_rays.npz")
+    off = g["traj_offsets"]
+    worst = 0.0
+    for i, row in enumerate(g["rows"]):
+        M, a, r_obs, al, oc, npts, nfev, status, tf = row
+        sol, outcome = gt.trace_ray(Kerr(float(M), float(a)), float(r_obs), float(al))
+        assert outcome == {1: "escaped", -1: "captured"}[int(oc)], i
+        assert sol.t.size == int(npts) and sol.nfev == int(nfev) and sol.status == int(status), i
+        np.testing.assert_array_equal(sol.y[:, 0], g["state0"][i])
+        e = np.abs(sol.y[:, -1] - g["y_final"][i]) / np.maximum(np.abs(g["y_final"][i]), FLOOR)
+        assert e.max() <= REL_TOL, (i, e)
+        assert abs(sol.t[-1] - tf) <= REL_TOL * max(1.0, tf)
+        sl = slice(off[i], off[i + 1])
+        assert np.abs(sol.t - g["traj_t"][sl]).max() <= 1e-7 * max(1.0, tf)
+        assert (np.abs(sol.y[1] - g["traj_r"][sl]) / g["traj_r"][sl]).max() <= 1e-7
+        worst = max(worst, e.max())
+    print("20 Kerr reference rays through the generic integrator: worst final-state rel err %.2e" % worst)
+    # several rays in one launch (plot_trajectories) and main.main(metric=Kerr)
+    res = gt.trace_paths(Kerr(1.0, 0.9), 50.0, np.radians([3.0, 10.0]))
+    assert [o for _, o in res] == ["captured", "escaped"]

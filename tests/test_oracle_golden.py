@@ -134,3 +134,16 @@ def test_kerr_golden_rays(oracle, golden):
         assert bits_equal(fa, g[p + "fa"]), k
         assert np.array_equal(w, g[p + "w"]) and np.array_equal(st, g[p + "status"]), k
         assert abs(oracle.kerr_r_plus(M, a) - row[5]) == 0.0
+
+
+def test_rk45_kerr_golden_rays(oracle, golden):
+    """scipy-RK45 restatement with Kerr.geodesic_equations (metrics.py:946-1029) against the
+    reference's geodesic_tracer.trace_ray(Kerr(...)): accepted points and nfev exact, event
+    point to 1e-11."""
+    g = golden("kerr_rk45_rays.npz")
+    for i, row in enumerate(g["rows"]):
+        M, a, r_obs, al, oc, npts, nfev, status, tf = row
+        r = oracle.rk45_integrate_kerr(float(M), float(a), g["state0"][i])
+        assert (r["outcome"], r["n_points"], r["nfev"], r["status"]) == (int(oc), int(npts), int(nfev), int(status)), i
+        assert abs(r["t_final"] - tf) <= 1e-11 * max(1.0, tf)
+        assert (np.abs(r["y_final"] - g["y_final"][i]) <= 1e-11 * np.maximum(np.abs(g["y_final"][i]), 1e-3)).all()
