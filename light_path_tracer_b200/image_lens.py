@@ -330,22 +330,29 @@ def render_lensed_image(source_image, alpha_lookup, final_alpha_lookup, winding_
 
 def render_frame(source_image, fov, r_obs, metric, psi=(0.0, 0.0), render_loop_around=False, *,
                  sampling=SAMPLE_NEAREST, rows=None, return_lookups=False, stats=None,
-                 flags=dev.TRACE_HYBRID, out=None, unit_u8=False):
+                 flags=dev.TRACE_HYBRID, out=None, unit_u8=False, theta_obs=np.pi / 2):
     """Fully fused device-resident frame (lp_render_frame): build_alpha_lookup +
     precompute_final_alpha_lookup + render_lensed_image in ONE launch, bit-identical to
     running the three stages back to back.  ``source_image`` is a CUDA tensor [H,W(,C)];
     ``rows=(row0, n_rows)`` renders a row tile (multi-GPU sharding).  Returns the CUDA
-    frame tensor (and the float32 / uint16 lookups with ``return_lookups``)."""
+    frame tensor (and the float32 / uint16 lookups with ``return_lookups``).
+
+    A ``Kerr`` metric takes the device-resident three-launch path (alpha lookup, Kerr tracer
+    with the per-pixel screen angle, remap) for the observer inclination ``theta_obs``; every
+    row of the tile is traced (no top/bottom mirror)."""
     t = dev.torch()
     e = _lib.ext()
-    if not isinstance(metric, Schwarzschild):
-        raise NotImplementedError("render_frame covers Schwarzschild metrics")
     height, width, channels = _source_layout(source_image)
     row0, n_rows = (0, height) if rows is None else rows
     src = source_image.contiguous()
     tile_shape = (n_rows, width) + tuple(source_image.shape[2:])
     if out is None:
         out = t.empty(tile_shape, dtype=src.dtype, device=src.device)
+    if isinstance(metric, Kerr):
+        return _render_frame_kerr(src, channels, fov, r_obs, metric, psi, render_loop_around, sampling,
+                                  (row0, n_rows), return_lookups, out, unit_u8, theta_obs)
+    if not isinstance(metric, Schwarzschild):
+        raise NotImplementedError("render_frame covers Schwarzschild and Kerr metrics")
     fa = w = None
     if return_lookups:
         fa = t.empty((n_rows, width), dtype=t.float32, device=src.device)
@@ -354,6 +361,24 @@ def render_frame(source_image, fov, r_obs, metric, psi=(0.0, 0.0), render_loop_a
     e.render_frame(src, channels, cam, int(row0), int(n_rows), float(metric.M), float(metric.R_S),
                    float(r_obs), dev.PHI_MAX, dev.H_MAX, bool(render_loop_around), int(sampling),
                    out, fa, w, stats, int(flags), bool(unit_u8))
+    if return_lookups:
+        return out, fa, w
+    return out
+
+
+def _render_frame_kerr(src, channels, fov, r_obs, metric, psi, loop_around, sampling, rows, return_lookups, out,
+                       unit_u8, theta_obs):
+    t = dev.torch()
+    e = _lib.ext()
+    height, width = int(src.shape[0]), int(src.shape[1])
+    row0, n_rows = rows
+    cam = dev.camera_vector((height, width), fov, psi, _psi_frame)
+    a32 = t.empty((n_rows, width), dtype=t.float32, device=src.device)
+    e.build_alpha_lookup(cam, int(row0), int(n_rows), -1, a32)
+    fx, _ = _focal((height, width), fov)
+    d_cols = dev.h2d(_axis_refine_columns(width, fx, psi).astype(np.uint8), "refine_cols")
+    fa, w = metric.trace_alpha_table_2d(a32, cam, r_obs, theta_obs, row0=row0, refine_cols=d_cols)
+    e.remap(src, channels, cam, fa, w, bool(loop_around), int(sampling), int(row0), int(n_rows), out, bool(unit_u8))
     if return_lookups:
         return out, fa, w
     return out

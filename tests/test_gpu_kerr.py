@@ -151,3 +151,31 @@ def test_kerr_device_tensors_and_zero_spin(native, oracle):
     fa_o, w_o, st_o, _ = oracle.kerr_trace_rays_batch(1.0, 0.0, 100.0, alpha, theta, np.pi / 2)
     assert np.array_equal(esc, np.isfinite(fa_o)) and np.array_equal(d_w.cpu().numpy(), w_o)
     m.trace_rays_batch(100.0, np.empty(0), np.empty(0), np.pi / 2, np.empty(0, dtype=bool), np.empty(0), np.empty(0, dtype=np.int64))
+
+
+def test_kerr_render_frame_and_tiles(native):
+    """render_frame / LensPipeline with a Kerr metric (device-resident alpha -> Kerr tracer ->
+    remap): equals the staged reference-facing calls on the same inputs, and row tiles equal the
+    corresponding rows of the full frame (multi-GPU sharding of Kerr frames)."""
+    import torch
+    from light_path_tracer_b200 import image_lens as il
+    m = _kerr(1.0, 0.8)
+    H, W = 60, 96
+    vfov = np.radians(16.0)
+    fov = (2 * np.arctan(np.tan(vfov / 2) * W / H), vfov)
+    psi, th_obs, r_obs = (0.01, -0.02), 1.1, 80.0
+    g = torch.Generator().manual_seed(4)
+    src = torch.rand(H, W, 3, generator=g)
+    full, fa, w = il.render_frame(src.cuda(), fov, r_obs, m, psi=psi, theta_obs=th_obs, return_lookups=True)
+    alpha = il.build_alpha_lookup((H, W), fov, psi=psi)
+    fa_s, w_s, n_total, n_traced = il.precompute_final_alpha_lookup_2d(alpha, fov, m.alpha_crit(r_obs, th_obs), r_obs, m,
+                                                                       theta_obs=th_obs, psi=psi)
+    assert n_total == n_traced == H * W
+    assert bits_equal(fa.cpu().numpy(), fa_s) and np.array_equal(w.cpu().numpy(), w_s)
+    staged = il.render_lensed_image(src.numpy(), alpha, fa_s, w_s, 0.0, fov, False, psi)
+    assert np.array_equal(full.cpu().numpy(), staged)
+    pipe = il.LensPipeline(src.cuda(), np.degrees(vfov), m)
+    for rows in ((0, 17), (17, 30), (47, 13)):
+        tile = il.render_frame(src.cuda(), fov, r_obs, m, psi=psi, theta_obs=th_obs, rows=rows)
+        assert torch.equal(tile, full[rows[0]:rows[0] + rows[1]])
+    assert pipe.render(r_obs, psi=psi).shape == (H, W, 3)
