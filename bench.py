@@ -353,7 +353,33 @@ def run_gpu(args):
         e8b.record()
         torch.cuda.synchronize()
         t_u8 = e8a.elapsed_time(e8b) / args.steps
+        # the other BASELINE configs that fit one GPU, one timed launch each after a warm-up:
+        # config 3 (generic 8-D RK45 integrator over the 4K alpha table) and a Kerr 4K lookup
+        from light_path_tracer_b200 import geodesic_tracer as gt
+        from light_path_tracer_b200.metrics import Kerr
+        a64 = a32.double()
+
+        def once(fn):
+            fn()
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record()
+            res = fn()
+            eb.record()
+            torch.cuda.synchronize()
+            return ea.elapsed_time(eb), res
+        t_rk45, rk = once(lambda: gt.trace_rays(metric, R_OBS, a64))
+        rk_attempts = float(((rk[3][..., 1].double() - 2) / 6).sum())
+        kerr = Kerr(M, 0.9)
+        cam_k = dev.camera_vector((H, W), fov, (0.0, 0.0), il._psi_frame)
+        t_kerr, _ = once(lambda: kerr.trace_alpha_table_2d(a32, cam_k, R_OBS, np.pi / 2))
         extra = {
+            "config3_rk45_frame_4k": {"ms": t_rk45, "rays_per_s": H * W / t_rk45 * 1e3,
+                                      "step_attempts_per_s": rk_attempts / t_rk45 * 1e3,
+                                      "what": "geodesic_tracer.trace_ray semantics (scipy RK45, rtol 1e-8) for every "
+                                              "pixel of the 3840x2160 alpha table, lp_rk45_kernel"},
+            "kerr_lookup_4k": {"ms": t_kerr, "rays_per_s": H * W / t_kerr * 1e3,
+                               "what": "Kerr a=0.9 M, equatorial observer: (alpha, theta) lookup of the full "
+                                       "3840x2160 frame without the top/bottom mirror, lp_kerr_kernel"},
             "e2e_u8_io": {"value": H * W / t_u8 * 1e3, "unit": "rays/s", "ms_per_frame": t_u8,
                           "h2d_bytes_per_step": int(src8_host.numel()), "d2h_bytes_per_step": int(out8[0].numel()),
                           "path": "as e2e, with the uint8 image boundary of image_lens.main (imread uint8 ... imsave "

@@ -12,6 +12,7 @@
 #include <stdlib.h>
 
 #define LP_TRACE_BLOCK 256          /* launch bound (max threads per CTA) */
+#define LP_RENDER_DEFAULT_TRIP 4
 #define LP_TRACE_DEFAULT_BLOCK 64   /* rays per CTA; LP_TRACE_BLOCK=32|64|128|256 overrides (tuning) */
 
 enum { SRC_F64 = 0, SRC_F32 = 1, SRC_CAM = 2 };
@@ -196,7 +197,7 @@ extern "C" int lp_schw_trace_frame(const lp_camera *h_cam, int32_t row0, int32_t
 // Same per-ray code as the kernels above followed by remap_pixel() on the float32-rounded
 // result, so the output is bit-identical to trace_frame + remap run back to back.
 // ---------------------------------------------------------------------------
-template <bool FUSED, bool FAST, typename T, int MINB>
+template <bool FUSED, bool FAST, typename T, int MINB, int TRIP>
 __global__ void __launch_bounds__(LP_TRACE_BLOCK, MINB)
 lp_render_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts c, const CamConsts cam)
 {
@@ -216,7 +217,7 @@ lp_render_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts c, con
         int row, col;
         pixel_row_col(i, a.n, cam.width, a.row0, row, col);
         const float a32 = (float)pixel_alpha64(cam, cam_x(cam, col), cam_y(cam, row));
-        binet_trace<FUSED, FAST>(c, L, (double)a32, r);
+        binet_trace<FUSED, FAST, TRIP>(c, L, (double)a32, r);
         if (FUSED && r.steps > a.retrace_steps) binet_trace<false, FAST>(c, L, (double)a32, r);
         const float fa32 = (float)((r.status == 1) ? r.fa : __longlong_as_double(0x7ff8000000000000LL));
         const long long nh = r.nh < 0 ? 0 : (r.nh > 65535 ? 65535 : r.nh);
@@ -251,6 +252,17 @@ static int render_minb()
     return cached;
 }
 
+// RK4 steps per loop trip of the FMA fast path: LP_RENDER_TRIP=2|4 (tuning knob).
+static int render_trip()
+{
+    static int cached = 0;
+    if (!cached) {
+        const char *e = getenv("LP_RENDER_TRIP");
+        cached = (e && atoi(e) == 2) ? 2 : (e && atoi(e) == 4) ? 4 : LP_RENDER_DEFAULT_TRIP;
+    }
+    return cached;
+}
+
 template <typename T, int MINB>
 static int launch_render_mb(const TraceArgs &a, const RemapArgs &ra, const BinetConsts &c,
                             const CamConsts &cam, uint32_t flags, cudaStream_t stream)
@@ -262,11 +274,12 @@ static int launch_render_mb(const TraceArgs &a, const RemapArgs &ra, const Binet
     if (chunks > 0x7fffffffLL) return LP_ERR_UNSUPPORTED;
     const unsigned grid = (unsigned)chunks;
     if (fused) {
-        if (icmp) lp_render_kernel<true, true, T, MINB><<<grid, block, 0, stream>>>(a, ra, c, cam);
-        else      lp_render_kernel<true, false, T, MINB><<<grid, block, 0, stream>>>(a, ra, c, cam);
+        if (icmp && render_trip() == 4) lp_render_kernel<true, true, T, MINB, 4><<<grid, block, 0, stream>>>(a, ra, c, cam);
+        else if (icmp) lp_render_kernel<true, true, T, MINB, 2><<<grid, block, 0, stream>>>(a, ra, c, cam);
+        else      lp_render_kernel<true, false, T, MINB, 2><<<grid, block, 0, stream>>>(a, ra, c, cam);
     } else {
-        if (icmp) lp_render_kernel<false, true, T, MINB><<<grid, block, 0, stream>>>(a, ra, c, cam);
-        else      lp_render_kernel<false, false, T, MINB><<<grid, block, 0, stream>>>(a, ra, c, cam);
+        if (icmp) lp_render_kernel<false, true, T, MINB, 2><<<grid, block, 0, stream>>>(a, ra, c, cam);
+        else      lp_render_kernel<false, false, T, MINB, 2><<<grid, block, 0, stream>>>(a, ra, c, cam);
     }
     return lp_check_launch();
 }
