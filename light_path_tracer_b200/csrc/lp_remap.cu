@@ -31,6 +31,28 @@ lp_remap_kernel(const RemapArgs a, const CamConsts cam)
 // the one-pixel-per-thread kernel (the remap is latency-, not bandwidth-limited otherwise).
 // Same per-pixel decisions as remap_pixel(), same integer source index.
 #define LP_REMAP4_BLOCK 128
+
+// sin and cos on [0, pi/2] (final_alpha of a sampled pixel is a float32 in that range): one
+// conditional reflection about pi/4 instead of a general quadrant reduction, the fdlibm kernel
+// polynomials with literal coefficients (compiler constant bank operands, nothing to load).
+__device__ __forceinline__ void sincos_first_quadrant(double x, double &s, double &c)
+{
+    const bool hi = x > 0.78539816339744828;                     // pi/4
+    // pi/2 - x with the low word of pi/2: exact enough for a float32-valued x
+    const double r = hi ? (1.5707963267948966 - x) + 6.123233995736766e-17 : x;
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    ps = fma(ps, z, 2.75573137070700676789e-06);   pc = fma(pc, z, -2.75573143513906633035e-07);
+    ps = fma(ps, z, -1.98412698298579493134e-04);  pc = fma(pc, z, 2.48015872894767294178e-05);
+    ps = fma(ps, z, 8.33333333332248946124e-03);   pc = fma(pc, z, -1.38888888888741095749e-03);
+    ps = fma(ps, z, -1.66666666666666324348e-01);  pc = fma(pc, z, 4.16666666666666019037e-02);
+    const double sr = fma(r * z, ps, r);
+    const double cr = fma(z * z, pc, fma(-0.5, z, 1.0));
+    s = hi ? cr : sr;
+    c = hi ? sr : cr;
+}
+
 __global__ void __launch_bounds__(LP_REMAP4_BLOCK)
 lp_remap_f32rgb_x4_kernel(const RemapArgs a, const CamConsts cam)
 {
@@ -44,18 +66,33 @@ lp_remap_f32rgb_x4_kernel(const RemapArgs a, const CamConsts cam)
     const float fa[4] = {fa4.x, fa4.y, fa4.z, fa4.w};
     const unsigned wn[4] = {w4.x, w4.y, w4.z, w4.w};
     const float *__restrict__ src = (const float *)a.src;
-    const long long H = cam.height, W = cam.width;
+    const int H = cam.height, W = cam.width;                 // the host checks H * W * 3 < 2^31 for this kernel
     float o[12];
-    long long off[4];
+    int off[4];
+    // row-constant parts of the two dot products A = v.e_x, B = v.e_y (v = (x_cam, y_cam, 1))
     const double yc = cam_y(cam, row);
-    // the four source directions, unconditionally (straight-line, interleavable); pixels that
-    // do not sample the source (captured, winding) run the math on a harmless angle
+    const double Ay = fma(yc, cam.ex1, cam.ex2), By = fma(yc, cam.ey1, cam.ey2);
     double px[4], py[4];
-    bool front[4], samp[4];
+    bool front[4];
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-        samp[p] = isfinite(fa[p]) && !(fa[p] > LP_HALF_PI_F32);
-        front[p] = source_coords_xy(cam, cam_x(cam, col + p), yc, samp[p] ? fa[p] : 0.5f, px[p], py[p]);
+        // straight-line (interleavable across the four pixels); pixels that do not sample the
+        // source (captured, winding) run the math on a harmless angle
+        const bool samp = fa[p] <= LP_HALF_PI_F32;               // false for NaN
+        const double xc = cam_x(cam, col + p);
+        const double A = fma(xc, cam.ex0, Ay), B = fma(xc, cam.ey0, By);
+        const double n2 = fmax(fma(A, A, B * B), 1e-300);        // the on-axis pixel itself is never sampled
+        const double inv = fast_rsqrt(n2);
+        const double st = A * inv, ct = B * inv;
+        double sf, cf;
+        sincos_first_quadrant(samp ? (double)fa[p] : 0.5, sf, cf);
+        const double sx = fma(cf, cam.d0, sf * fma(st, cam.ex0, ct * cam.ey0));
+        const double sy = fma(cf, cam.d1, sf * fma(st, cam.ex1, ct * cam.ey1));
+        const double sz = fma(cf, cam.d2, sf * fma(st, cam.ex2, ct * cam.ey2));
+        front[p] = sz > 1e-12;
+        const double isz = fast_rcp(front[p] ? sz : 1.0);
+        px[p] = fma(sx * isz, cam.fx, cam.half_w);
+        py[p] = fma(sy * isz, cam.fy, cam.half_h);
     }
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
@@ -67,10 +104,18 @@ lp_remap_f32rgb_x4_kernel(const RemapArgs a, const CamConsts cam)
             const unsigned k = wn[p] > 4u ? 4u : wn[p];
             o[3 * p] = c_wind_rgb[k][0]; o[3 * p + 1] = c_wind_rgb[k][1]; o[3 * p + 2] = c_wind_rgb[k][2];
         } else {
-            long long ix = (long long)rint(px[p]), iy = (long long)rint(py[p]);
+            // np.rint -> index; cvt.rni.s32.f64 rounds half to even and saturates, so a far
+            // out-of-frame coordinate stays out of frame
+            int ix = __double2int_rn(front[p] ? px[p] : cam.half_w);       // image_lens.py:356-361
+            int iy = __double2int_rn(front[p] ? py[p] : cam.half_h);
             bool ok;
-            if (a.loop_around) { ix = pymod(ix, W); iy = pymod(iy, H); ok = true; }
-            else ok = front[p] && iy >= 0 && iy < H && ix >= 0 && ix < W;
+            if (a.loop_around) {
+                ix %= W; ix += (ix < 0) ? W : 0;
+                iy %= H; iy += (iy < 0) ? H : 0;
+                ok = true;
+            } else {
+                ok = front[p] && (unsigned)ix < (unsigned)W && (unsigned)iy < (unsigned)H;
+            }
             if (ok) off[p] = (iy * W + ix) * 3;
             else { o[3 * p] = 1.0f; o[3 * p + 1] = 0.0f; o[3 * p + 2] = 1.0f; }
         }
@@ -111,6 +156,7 @@ extern "C" int lp_remap(const void *src, int32_t src_dtype, int32_t channels,
     if (!src || !out || !fa32) return LP_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (src_dtype == LP_DTYPE_F32 && channels == 3 && sampling == LP_SAMPLE_NEAREST && cam.width % 4 == 0 &&
+        (long long)cam.height * cam.width * 3 < 0x7fffffffLL &&
         ((uintptr_t)out % 16) == 0 && ((uintptr_t)fa32 % 16) == 0 && (!w16 || ((uintptr_t)w16 % 8) == 0)) {
         const long long quads = a.n / 4;                 // width % 4 == 0 -> n % 4 == 0
         const long long blocks = (quads + LP_REMAP4_BLOCK - 1) / LP_REMAP4_BLOCK;
