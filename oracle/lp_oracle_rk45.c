@@ -36,7 +36,7 @@
 #define MIN_FACTOR 0.2
 #define MAX_FACTOR 10.0
 
-static const double C_[6] = {0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1};
+/* (the nodes C are not needed: the right-hand sides are autonomous) */
 static const double A_[6][5] = {
     {0, 0, 0, 0, 0},
     {1.0 / 5, 0, 0, 0, 0},
