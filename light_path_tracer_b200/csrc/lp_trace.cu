@@ -38,11 +38,16 @@ struct TraceArgs {
 // final_alpha with identical status and n_half_orbits; 192 (phi <= 9.6, <= 1e-12) leaves two
 // orders of margin to the 1e-9 parity bound, and in a 4K frame only ~1e-4 of the rays are
 // longer than that (they are the ones the strict retrace exists for).
-#define LP_HYBRID_RETRACE_STEPS 192
+// (what matters is the swept angle, 192 steps x 0.05 rad = 9.6 rad: for another step size the
+// threshold is the number of steps that sweeps the same angle)
+#define LP_HYBRID_RETRACE_PHI 9.6
 
-static int retrace_steps_for(uint32_t flags)
+static int retrace_steps_for(uint32_t flags, double h_max)
 {
-    return (flags & LP_TRACE_HYBRID) ? LP_HYBRID_RETRACE_STEPS : 0x7fffffff;
+    if (!(flags & LP_TRACE_HYBRID)) return 0x7fffffff;
+    if (!(h_max > 0.0)) return 0;                       // degenerate step: everything strict
+    const double k = floor(LP_HYBRID_RETRACE_PHI / h_max + 1e-9);
+    return k < 1.0 ? 0 : (k > 1.0e9 ? 0x7fffffff : (int)k);
 }
 
 // One ray per thread, one CTA per `blockDim.x` consecutive rays.  The grid is NOT
@@ -143,7 +148,7 @@ extern "C" int lp_schw_trace_batch_f64(const double *alphas, int64_t n,
     if (rc != LP_OK) return rc;
     CamConsts cam = {};
     TraceArgs a = {};
-    a.retrace_steps = retrace_steps_for(flags);
+    a.retrace_steps = retrace_steps_for(flags, h_max);
     a.alphas = alphas; a.n = n; a.out_fa = out_fa; a.out_w = out_w;
     a.out_status = out_status; a.out_steps = out_steps; a.stats = stats;
     return launch_trace<SRC_F64, true>(a, c, cam, flags, (cudaStream_t)stream);
@@ -163,7 +168,7 @@ extern "C" int lp_schw_trace_alpha32(const float *alpha32, int64_t n,
     if (rc != LP_OK) return rc;
     CamConsts cam = {};
     TraceArgs a = {};
-    a.retrace_steps = retrace_steps_for(flags);
+    a.retrace_steps = retrace_steps_for(flags, h_max);
     a.alphas = alpha32; a.n = n; a.out_fa = out_fa32; a.out_w = out_w16;
     a.out_status = out_status; a.out_steps = out_steps; a.stats = stats;
     return launch_trace<SRC_F32, false>(a, c, cam, flags, (cudaStream_t)stream);
@@ -186,7 +191,7 @@ extern "C" int lp_schw_trace_frame(const lp_camera *h_cam, int32_t row0, int32_t
     rc = lp_make_binet_consts(M, R_S, r_obs, phi_max, h_max, &c);
     if (rc != LP_OK) return rc;
     TraceArgs a = {};
-    a.retrace_steps = retrace_steps_for(flags);
+    a.retrace_steps = retrace_steps_for(flags, h_max);
     a.n = n; a.out_fa = out_fa32; a.out_w = out_w16; a.out_alpha32 = out_alpha32;
     a.out_status = out_status; a.out_steps = out_steps; a.stats = stats; a.row0 = row0;
     return launch_trace<SRC_CAM, false>(a, c, cam, flags, (cudaStream_t)stream);
@@ -312,7 +317,7 @@ extern "C" int lp_render_frame(const void *src, int32_t src_dtype, int32_t chann
     rc = lp_make_binet_consts(M, R_S, r_obs, phi_max, h_max, &c);
     if (rc != LP_OK) return rc;
     TraceArgs a = {};
-    a.retrace_steps = retrace_steps_for(flags);
+    a.retrace_steps = retrace_steps_for(flags, h_max);
     a.n = n; a.out_fa = out_fa32; a.out_w = out_w16; a.stats = stats; a.row0 = row0;
     RemapArgs ra;
     ra.src = src; ra.out = out; ra.fa32 = nullptr; ra.w16 = nullptr; ra.n = n;
