@@ -66,14 +66,12 @@ def build_lib(force=False, verbose=False, ptxas_info=False):
     os.makedirs(OUT, exist_ok=True)
     srcs = [os.path.join(CSRC, s) for s in CU_SOURCES]
     deps = srcs + [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS] + [__file__]
-    log = ""
-    objs = []
-    for s in srcs:
-        o = os.path.join(OUT, os.path.basename(s)[:-3] + ".o")
-        objs.append(o)
-        if force or _stale(o, deps):
-            cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_info else []) + ["-c", s, "-o", o]
-            log += _run(cmd, verbose)
+    from concurrent.futures import ThreadPoolExecutor
+    objs = [os.path.join(OUT, os.path.basename(s)[:-3] + ".o") for s in srcs]
+    jobs = [[_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_info else []) + ["-c", s, "-o", o]
+            for s, o in zip(srcs, objs) if force or _stale(o, deps)]
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as pool:
+        log = "".join(pool.map(lambda cmd: _run(cmd, verbose), jobs))
     if force or _stale(LIB, objs):
         _run([_nvcc(), "-shared", "-o", LIB] + objs, verbose)
     return log
