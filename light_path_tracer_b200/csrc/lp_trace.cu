@@ -244,19 +244,6 @@ lp_render_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts c, con
     }
 }
 
-// MINB = CTAs of LP_TRACE_BLOCK threads ptxas must fit per SM: 4 -> 64 registers (32 warps/SM),
-// 5 -> 48 registers (40 warps/SM, a few spills outside the loop).  LP_RENDER_MINB=5 selects the
-// second build (tuning knob).
-static int render_minb()
-{
-    static int cached = 0;
-    if (!cached) {
-        const char *e = getenv("LP_RENDER_MINB");
-        cached = (e && atoi(e) == 5) ? 5 : 4;
-    }
-    return cached;
-}
-
 // RK4 steps per loop trip of the FMA fast path: LP_RENDER_TRIP=2|4 (tuning knob).
 static int render_trip()
 {
@@ -289,11 +276,12 @@ static int launch_render_mb(const TraceArgs &a, const RemapArgs &ra, const Binet
     return lp_check_launch();
 }
 
+// MINB = 4 CTAs of LP_TRACE_BLOCK threads per SM -> ptxas keeps the kernel at 64 registers
+// (32 warps/SM); a 48-register build (40 warps/SM, spills outside the loop) measured 1 % slower.
 template <typename T>
 static int launch_render(const TraceArgs &a, const RemapArgs &ra, const BinetConsts &c,
                          const CamConsts &cam, uint32_t flags, cudaStream_t stream)
 {
-    if (render_minb() == 5) return launch_render_mb<T, 5>(a, ra, c, cam, flags, stream);
     return launch_render_mb<T, 4>(a, ra, c, cam, flags, stream);
 }
 
