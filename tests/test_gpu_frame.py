@@ -342,3 +342,39 @@ def test_unit_u8_boundary(native, golden, oracle, tag):
     fa_g, w_g = fa_g.cpu().numpy(), w_g.cpu().numpy()
     ref2 = (oracle.render_lensed_image(src_f, fa_g, w_g, fov, False, psi) * 255).astype(np.uint8)
     assert np.array_equal(frame.cpu().numpy(), ref2)
+
+
+def test_frame_4k_vs_oracle(native, oracle):
+    """The bench workload itself (3840x2160, r_obs = 100 M, 40 deg, float32 RGB checkerboard)
+    against the oracle at FULL size: alpha table, lookups (strict AND hybrid arithmetic), remap
+    and the fused frame in 8 bit."""
+    import torch
+    il = _il()
+    H, W = 2160, 3840
+    vfov = np.radians(40.0)
+    fov = (2 * np.arctan(np.tan(vfov / 2) * W / H), vfov)
+    metric = _metric(1.0)
+    a_ref = oracle.build_alpha_lookup((H, W), fov)
+    a = il.build_alpha_lookup((H, W), fov)
+    d = _f32_ulp_diff(a, a_ref)
+    assert d.max() <= 1 and (d > 0).sum() <= 64
+    fa_ref, w_ref, _, _ = oracle.precompute_final_alpha_lookup(a_ref, 1.0, 100.0)
+    d_a = torch.from_numpy(a_ref).cuda()
+    for flags in (0, 4):
+        fa, w = metric.trace_alpha_table(d_a, 100.0, flags=flags)
+        fa, w = fa.cpu().numpy(), w.cpu().numpy()
+        assert np.array_equal(np.isnan(fa), np.isnan(fa_ref)), "classification differs (flags=%d)" % flags
+        assert np.array_equal(w, w_ref), "winding differs (flags=%d)" % flags
+        d = _f32_ulp_diff(fa, fa_ref)
+        print("4K lookups, flags=%d: %d of %d float32 final_alpha values differ (max %d step)" % (
+            flags, int((d > 0).sum()), d.size, int(d.max())))
+        assert d.max() <= 1 and (d > 0).sum() <= 64
+    src = oracle.checkerboard(H, W)
+    ref = oracle.render_lensed_image(src, fa_ref, w_ref, fov)
+    out = il.render_lensed_image(torch.from_numpy(src).cuda(), None, torch.from_numpy(fa_ref).cuda(),
+                                 torch.from_numpy(w_ref).cuda(), 0.0, fov).cpu().numpy()
+    assert np.array_equal(out, ref), "%d remapped pixels differ" % int((out != ref).any(-1).sum())
+    fused = il.render_frame(torch.from_numpy(src).cuda(), fov, 100.0, metric).cpu().numpy()
+    bad = (np.abs(np.floor(fused * 255) - np.floor(ref * 255)) > 1).any(-1)
+    print("4K fused frame: %d pixels differ by more than 1/255 from the reference pipeline" % int(bad.sum()))
+    assert bad.sum() <= 16
