@@ -23,6 +23,7 @@
 
 #define KERR_BLOCK 128
 #define KERR_REFILL_MIN 4
+#define KERR_DEFAULT_MINB 4
 
 struct KerrArgs {
     // ray source A: explicit arrays
@@ -52,8 +53,8 @@ static __constant__ double kA21 = 1.0 / 5.0, kA31 = 3.0 / 40.0, kA32 = 9.0 / 40.
 // metrics.py:227-306.  EXACT: the reference's expression tree with one IEEE division per `/`;
 // otherwise the same expressions over three shared reciprocals (see below).
 template <bool EXACT>
-__device__ __forceinline__ void kerr_rhs(const double (&s)[5], double p_t, double p_phi, double M, double a,
-                                         double r_floor, double (&out)[5])
+__device__ __noinline__ void kerr_rhs(const double (&s)[5], double p_t, double p_phi, double M, double a,
+                                      double r_floor, double (&out)[5])
 {
     const double r = s[0], th = s[1], p_r = s[3], p_th = s[4];
     if (r <= r_floor) {
@@ -289,8 +290,8 @@ __device__ __forceinline__ double pixel_theta(const CamConsts &cam, int row, int
     return atan2(vx * cam.ex0 + vy * cam.ex1 + vz * cam.ex2, vx * cam.ey0 + vy * cam.ey1 + vz * cam.ey2);
 }
 
-template <bool EXACT>
-__global__ void __launch_bounds__(KERR_BLOCK, 2)
+template <bool EXACT, int MINB>
+__global__ void __launch_bounds__(KERR_BLOCK, MINB)
 lp_kerr_kernel(const KerrArgs a, const CamConsts cam)
 {
     const unsigned full = 0xffffffffu;
@@ -466,13 +467,30 @@ static int kerr_launch(KerrArgs &a, const CamConsts &cam, cudaStream_t stream)
 {
     if (a.n == 0) return LP_OK;
     const bool fast = kerr_fast_rhs();
-    int grid = 0;
-    int rc = lp_grid_for(fast ? (const void *)lp_kerr_kernel<false> : (const void *)lp_kerr_kernel<true>, KERR_BLOCK, &grid);
-    if (rc != LP_OK) return rc;
-    const long long chunks = (a.n + KERR_BLOCK - 1) / KERR_BLOCK;
-    if (chunks < grid) grid = (int)chunks;
-    if (fast) lp_kerr_kernel<false><<<grid, KERR_BLOCK, 0, stream>>>(a, cam);
-    else      lp_kerr_kernel<true><<<grid, KERR_BLOCK, 0, stream>>>(a, cam);
+    // resident CTAs per SM ptxas must fit (register cap): the kernel is latency-bound, so more
+    // resident warps win until the spills cost more (LP_KERR_MINB = 2..6, tuning knob)
+    static int minb = 0;
+    if (!minb) {
+        const char *e = getenv("LP_KERR_MINB");
+        const int v = e ? atoi(e) : 0;
+        minb = (v >= 2 && v <= 6) ? v : KERR_DEFAULT_MINB;
+    }
+#define KERR_DISPATCH(EX, MB) \
+    do { \
+        int grid = 0; \
+        int rc = lp_grid_for((const void *)lp_kerr_kernel<EX, MB>, KERR_BLOCK, &grid); \
+        if (rc != LP_OK) return rc; \
+        const long long chunks = (a.n + KERR_BLOCK - 1) / KERR_BLOCK; \
+        if (chunks < grid) grid = (int)chunks; \
+        lp_kerr_kernel<EX, MB><<<grid, KERR_BLOCK, 0, stream>>>(a, cam); \
+    } while (0)
+    if (fast) { KERR_DISPATCH(false, 2); }
+    else if (minb == 2) { KERR_DISPATCH(true, 2); }
+    else if (minb == 3) { KERR_DISPATCH(true, 3); }
+    else if (minb == 4) { KERR_DISPATCH(true, 4); }
+    else if (minb == 5) { KERR_DISPATCH(true, 5); }
+    else { KERR_DISPATCH(true, 6); }
+#undef KERR_DISPATCH
     return lp_check_launch();
 }
 

@@ -36,6 +36,14 @@ for _ in range(reps):
         f2 = (2 * np.arctan(np.tan(vfov / 2) * w_ / h), vfov)
         a = il.build_alpha_lookup((h, w_), f2, device=True).double()
         gt.trace_rays(m, 100.0, a)
+    elif case == "kerr":
+        from light_path_tracer_b200.metrics import Kerr
+        from light_path_tracer_b200 import _device as dev
+        h, w_ = 540, 960
+        f2 = (2 * np.arctan(np.tan(vfov / 2) * w_ / h), vfov)
+        a = il.build_alpha_lookup((h, w_), f2, device=True)
+        cam = dev.camera_vector((h, w_), f2, (0.0, 0.0), il._psi_frame)
+        Kerr(1.0, 0.9).trace_alpha_table_2d(a, cam, 100.0, np.pi / 2)
     elif case == "shadow":
         bs.shadow_image(m, 4096, 4096, np.radians(40), 50.0, device=True)
 torch.cuda.synchronize()
