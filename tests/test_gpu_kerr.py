@@ -179,3 +179,42 @@ def test_kerr_render_frame_and_tiles(native):
         tile = il.render_frame(src.cuda(), fov, r_obs, m, psi=psi, theta_obs=th_obs, rows=rows)
         assert torch.equal(tile, full[rows[0]:rows[0] + rows[1]])
     assert pipe.render(r_obs, psi=psi).shape == (H, W, 3)
+
+
+def test_kerr_views_tensor_lookup_and_odd_inputs(native, oracle):
+    """Slices / strided outputs written in place (the reference passes arr[start:end]); CUDA-tensor
+    form of the 2-D lookup equals the numpy form; NaN / negative / > pi/2 angles behave like the
+    oracle (status, winding)."""
+    import torch
+    from light_path_tracer_b200 import image_lens as il
+    m = _kerr(1.0, 0.6)
+    rng = np.random.default_rng(8)
+    alpha = rng.uniform(0, 0.3, 700)
+    theta = rng.uniform(-3, 3, 700)
+    big_fa = np.full(1000, -5.0)
+    big_w = np.full(1000, -5, dtype=np.int64)
+    m.trace_rays_batch(70.0, alpha[50:400], theta[50:400], 1.0, np.zeros(350, dtype=bool), big_fa[100:450], big_w[100:450])
+    assert (big_fa[:100] == -5).all() and (big_fa[450:] == -5).all() and (big_w[450:] == -5).all()
+    fa_o, w_o, _, _ = oracle.kerr_trace_rays_batch(1.0, 0.6, 70.0, alpha[50:400], theta[50:400], 1.0)
+    assert np.array_equal(np.isnan(big_fa[100:450]), np.isnan(fa_o)) and np.array_equal(big_w[100:450], w_o)
+    fa2 = np.full(700, -1.0)
+    w2 = np.full(700, -1, dtype=np.int64)
+    m.trace_rays_batch(70.0, alpha[::2], theta[::2], 1.0, None, fa2[::2], w2[::2])
+    assert (fa2[1::2] == -1).all()
+    odd = np.array([np.nan, -0.1, 2.0, 3.1, 0.0, 1e-300])
+    st = np.empty(odd.size, dtype=np.int8)
+    fa3 = np.empty(odd.size)
+    w3 = np.empty(odd.size, dtype=np.int64)
+    m.trace_rays_batch(70.0, odd, np.full(odd.size, 0.7), 1.0, None, fa3, w3, status=st)
+    fa_o, w_o, st_o, _ = oracle.kerr_trace_rays_batch(1.0, 0.6, 70.0, odd, np.full(odd.size, 0.7), 1.0)
+    assert np.array_equal(st[1:], st_o[1:]) and np.array_equal(w3[1:], w_o[1:])     # NaN alpha: int(nan) is undefined upstream
+    # tensor form of the 2-D lookup
+    H, W = 40, 64
+    vfov = np.radians(15.0)
+    fov = (2 * np.arctan(np.tan(vfov / 2) * W / H), vfov)
+    a = il.build_alpha_lookup((H, W), fov)
+    fa_n, w_n, nt, ntr = il.precompute_final_alpha_lookup_2d(a, fov, 0.0, 70.0, m)
+    fa_t, w_t, nt2, ntr2 = il.precompute_final_alpha_lookup_2d(torch.from_numpy(a).cuda(), fov, 0.0, 70.0, m)
+    assert (nt, ntr) == (nt2, ntr2) == (H * W, H * W // 2)
+    assert bits_equal(fa_n, fa_t.cpu().numpy()) and np.array_equal(w_n, w_t.cpu().numpy())
+    assert bits_equal(fa_n[H - H // 2:], fa_n[:H // 2][::-1])                     # top/bottom mirror
