@@ -14,6 +14,11 @@ from conftest import bits_equal
 pytestmark = pytest.mark.gpu
 
 REL_TOL = 1e-9
+# Absolute floor of the relative bar: final_alpha = arccos(c) with c a double
+# is quantised in steps of ulp(c)/sin(final_alpha); below ~1e-3 (pixels on an Einstein ring, and
+# the mirror case near pi) the reference's own value carries that quantum, which exceeds 1e-9
+# relative, so the bar is |delta| <= 1e-9 * max(final_alpha, 1e-3).
+FA_FLOOR = 1e-3
 
 
 def _metrics():
@@ -45,7 +50,7 @@ def _check_batch(M, r_obs, alpha, fa_ref, w_ref, fa, w, what, oracle=None):
     flips = (esc_ref != esc)
     same = esc_ref & esc
     err = np.zeros(alpha.size)
-    err[same] = np.abs(fa[same] - fa_ref[same]) / np.abs(fa_ref[same])
+    err[same] = np.abs(fa[same] - fa_ref[same]) / np.maximum(np.abs(fa_ref[same]), FA_FLOOR)
     suspect = (flips & ~in_band) | (same & (err > REL_TOL)) | (~flips & (w != w_ref))
     n_sens = 0
     if suspect.any():
@@ -63,7 +68,7 @@ def _check_batch(M, r_obs, alpha, fa_ref, w_ref, fa, w, what, oracle=None):
                 ok = any(wn == w[i] for _, wn in neighbours) or w[i] == w_ref[i]
                 if ref_esc:
                     spread = max([abs(f - fa_ref[i]) for f, _ in neighbours if np.isfinite(f)] + [0.0])
-                    ok = ok and abs(fa[i] - fa_ref[i]) <= REL_TOL * abs(fa_ref[i]) + 1.5 * spread
+                    ok = ok and abs(fa[i] - fa_ref[i]) <= REL_TOL * max(abs(fa_ref[i]), FA_FLOOR) + 1.5 * spread
             assert ok, "%s: alpha=%r: gpu (%r, %d) vs reference (%r, %d), neighbours %r" % (
                 what, alpha[i], fa[i], w[i], fa_ref[i], w_ref[i], neighbours)
         n_sens = idx.size
