@@ -35,6 +35,7 @@ struct KerrArgs {
     int32_t frame_mode, row0;
     long long n;
     double M, a, r_plus, r_obs, theta_obs, lambda_max;
+    double sin_th_obs, cos_th_obs;   // host libm (the reference's own), one value per launch
     // outputs (WIDE: f64 / i64, else f32 / u16)
     void *out_fa, *out_w;
     int32_t wide;
@@ -199,11 +200,10 @@ __device__ __forceinline__ void kerr_dp_stages(const double (&state)[5], const d
 
 // metrics.py:148-224.  false = (ok == False) -> status 0.
 __device__ __forceinline__ bool kerr_init(double M, double a, double r_obs, double alpha, double theta,
-                                          double theta_obs, double (&state)[5], double &p_t, double &p_phi)
+                                          double theta_obs, double sin_th, double cos_th,
+                                          double (&state)[5], double &p_t, double &p_phi)
 {
     const double r = r_obs, th = theta_obs;
-    double sin_th, cos_th;
-    sincos(th, &sin_th, &cos_th);
     double sin_th_sq = sin_th * sin_th;
     if (sin_th_sq < 1e-15) sin_th_sq = 1e-15;
     const double Sigma = r * r + a * a * cos_th * cos_th;
@@ -340,7 +340,7 @@ lp_kerr_kernel(const KerrArgs a, const CamConsts cam)
                 }
                 atol = refine ? 1e-10 : 1e-8;                               // metrics.py:432-433
                 rtol = refine ? 1e-8 : 1e-6;
-                if (kerr_init(M, sp, a.r_obs, alpha, theta, a.theta_obs, state, p_t, p_phi)) {
+                if (kerr_init(M, sp, a.r_obs, alpha, theta, a.theta_obs, a.sin_th_obs, a.cos_th_obs, state, p_t, p_phi)) {
                     kerr_rhs<EXACT>(state, p_t, p_phi, M, sp, r_floor, k1);   // FSAL seed, metrics.py:447
                     lam = 0.0;
                     h = fmax(1.0, 0.01 * a.r_obs);
@@ -466,6 +466,8 @@ static bool kerr_fast_rhs()
 static int kerr_launch(KerrArgs &a, const CamConsts &cam, cudaStream_t stream)
 {
     if (a.n == 0) return LP_OK;
+    a.sin_th_obs = sin(a.theta_obs);
+    a.cos_th_obs = cos(a.theta_obs);
     const bool fast = kerr_fast_rhs();
     // resident CTAs per SM ptxas must fit (register cap): the kernel is latency-bound, so more
     // resident warps win until the spills cost more (LP_KERR_MINB = 2..6, tuning knob)

@@ -75,6 +75,8 @@ def lib():
         L.lp_oracle_kerr_trace_ray.argtypes = [d, d, d, d, d, d, d, d, ctypes.c_int, vp, vp, vp]
         L.lp_oracle_kerr_trace_batch.restype = None
         L.lp_oracle_kerr_trace_batch.argtypes = [d, d, d, d, vp, vp, d, d, vp, i64, vp, vp, vp, vp]
+        L.lp_oracle_kerr_trace_batch_trigshift.restype = None
+        L.lp_oracle_kerr_trace_batch_trigshift.argtypes = [d, d, d, d, vp, vp, d, d, vp, i64, ctypes.c_int, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -226,9 +228,11 @@ def kerr_lambda_max(r_obs):
     return max(5000.0, 6.0 * r_obs)                       # metrics.py:1120, :1131
 
 
-def kerr_trace_rays_batch(M, a, r_obs, alphas, thetas, theta_obs, axis_refines=None, lambda_max=None):
+def kerr_trace_rays_batch(M, a, r_obs, alphas, thetas, theta_obs, axis_refines=None, lambda_max=None,
+                          trig_shift=0):
     """Kerr.trace_rays_batch (metrics.py:1128-1132) -> (out_fa f64[n], out_w i64[n], status i8[n],
-    steps i32[n, 2] = (accepted, attempts))."""
+    steps i32[n, 2] = (accepted, attempts)).  ``trig_shift`` != 0 is a sensitivity probe, not a
+    reference path: sin/cos(theta) in the right-hand side moved by that many ulps."""
     alphas = np.ascontiguousarray(alphas, dtype=np.float64)
     thetas = np.ascontiguousarray(thetas, dtype=np.float64)
     n = alphas.size
@@ -238,8 +242,13 @@ def kerr_trace_rays_batch(M, a, r_obs, alphas, thetas, theta_obs, axis_refines=N
     st = np.empty(n, np.int8)
     steps = np.empty((n, 2), np.int32)
     lam = kerr_lambda_max(r_obs) if lambda_max is None else lambda_max
-    lib().lp_oracle_kerr_trace_batch(M, a, float(kerr_r_plus(M, a)), r_obs, _p(alphas), _p(thetas), theta_obs, lam,
-                                     _p(ar), n, _p(fa), _p(w), _p(st), _p(steps))
+    if trig_shift:
+        lib().lp_oracle_kerr_trace_batch_trigshift(M, a, float(kerr_r_plus(M, a)), r_obs, _p(alphas), _p(thetas),
+                                                   theta_obs, lam, _p(ar), n, int(trig_shift), _p(fa), _p(w),
+                                                   _p(st), _p(steps))
+    else:
+        lib().lp_oracle_kerr_trace_batch(M, a, float(kerr_r_plus(M, a)), r_obs, _p(alphas), _p(thetas), theta_obs,
+                                         lam, _p(ar), n, _p(fa), _p(w), _p(st), _p(steps))
     return fa, w, st, steps
 
 

@@ -87,12 +87,46 @@ static int kerr_initial_conditions(double M, double a, double r_obs, double alph
     return 1;
 }
 
+/* Sensitivity probe (NOT a reference path): every sin / cos of theta in the right-hand side moved
+ * by g_trig_shift ulps.  The reference calls the host libm there; another libm (or CUDA's) differs
+ * from it by an ulp in a few percent of the calls, and the adaptive controller turns such ulps
+ * into ~1e-9..1e-8 of final_alpha for some rays (rtol 1e-8 makes the error norm a 9-digit
+ * cancellation).  The tests use this to measure, per ray, how far the REFERENCE's own result
+ * moves under that kind of perturbation. */
+static __thread int g_trig_shift = 0;      /* probe pattern, see trig_probe() */
+static __thread unsigned g_trig_calls = 0;
+
+static double nudge(double x, int k)
+{
+    for (; k > 0; --k) x = nextafter(x, INFINITY);
+    for (; k < 0; ++k) x = nextafter(x, -INFINITY);
+    return x;
+}
+
+/* probe patterns: 1 / 2: sin and cos one ulp apart in opposite directions, every call;
+ * 3: sin + 1 ulp; 4: cos + 1 ulp; 5: both, sign alternating from call to call;
+ * 6: every 7th call only (a sparse error pattern, like a libm that is off in a few % of calls) */
+static void trig_probe(double *s, double *c)
+{
+    const unsigned k = g_trig_calls++;
+    switch (g_trig_shift) {
+    case 1: *s = nudge(*s, 1); *c = nudge(*c, -1); break;
+    case 2: *s = nudge(*s, -1); *c = nudge(*c, 1); break;
+    case 3: *s = nudge(*s, 1); break;
+    case 4: *c = nudge(*c, 1); break;
+    case 5: { const int d = (k & 1) ? 1 : -1; *s = nudge(*s, d); *c = nudge(*c, d); break; }
+    case 6: if (k % 7 == 3) { *s = nudge(*s, 1); *c = nudge(*c, 1); } break;
+    default: break;
+    }
+}
+
 /* metrics.py:227-306 */
 static void kerr_rhs(const double *s, double p_t, double p_phi, double M, double a, double r_plus, double *out)
 {
     const double r = s[0], th = s[1], p_r = s[3], p_th = s[4];
     if (r <= r_plus * 1.001) { for (int i = 0; i < 5; ++i) out[i] = 0.0; return; }
-    const double sin_th = sin(th), cos_th = cos(th);
+    double sin_th = sin(th), cos_th = cos(th);
+    if (g_trig_shift) trig_probe(&sin_th, &cos_th);
     double sin_th_sq = sin_th * sin_th;
     if (sin_th_sq < 1e-15) sin_th_sq = 1e-15;
     const double Sigma = r * r + a * a * cos_th * cos_th;
@@ -296,6 +330,26 @@ void lp_oracle_kerr_trace_batch(double M, double a, double r_plus, double r_obs,
         double fa; int64_t nh; int32_t st[2];
         const int s = lp_oracle_kerr_trace_ray(M, a, r_plus, r_obs, alphas[i], thetas[i], theta_obs, lambda_max,
                                                axis_refines ? axis_refines[i] : 0, &fa, &nh, st);
+        out_fa[i] = (s == 1) ? fa : NAN;
+        out_w[i] = nh;
+        if (out_status) out_status[i] = (int8_t)s;
+        if (out_steps) { out_steps[2 * i] = st[0]; out_steps[2 * i + 1] = st[1]; }
+    }
+}
+
+/* lp_oracle_kerr_trace_batch with the trig-shift probe switched on (see g_trig_shift). */
+void lp_oracle_kerr_trace_batch_trigshift(double M, double a, double r_plus, double r_obs,
+                                          const double *alphas, const double *thetas, double theta_obs,
+                                          double lambda_max, const uint8_t *axis_refines, int64_t n, int shift,
+                                          double *out_fa, int64_t *out_w, int8_t *out_status, int32_t *out_steps)
+{
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t i = 0; i < n; ++i) {
+        double fa; int64_t nh; int32_t st[2];
+        g_trig_shift = shift; g_trig_calls = 0;
+        const int s = lp_oracle_kerr_trace_ray(M, a, r_plus, r_obs, alphas[i], thetas[i], theta_obs, lambda_max,
+                                               axis_refines ? axis_refines[i] : 0, &fa, &nh, st);
+        g_trig_shift = 0;
         out_fa[i] = (s == 1) ? fa : NAN;
         out_w[i] = nh;
         if (out_status) out_status[i] = (int8_t)s;

@@ -8,8 +8,10 @@ Bar: classification and winding exact, final_alpha within 1e-9 relative — for 
 accept/reject sequence the kernel reproduces (the integrator is adaptive with rtol = 1e-6: a
 borderline error norm can flip ONE accept/reject decision, after which the two integrations
 differ by the method's own tolerance, not by rounding; such rays are counted and bounded), plus
-the conditioning clause measured with the oracle itself (how far the reference's own result
-moves when alpha moves by one ulp).
+the conditioning clause measured with the oracle itself: how far the reference's own result
+moves when alpha moves by one ulp, or when the sin/cos(theta) calls of its right-hand side are
+one ulp off in six different patterns (what a different libm does); the GPU result must lie
+within 1e-9 plus three times the largest of those movements.
 """
 import numpy as np
 import pytest
@@ -29,11 +31,16 @@ def _kerr(M, a):
 def _check(oracle, M, a, r_obs, th_obs, alpha, theta, refine, fa, w, st, steps, what):
     fa_o, w_o, st_o, steps_o = oracle.kerr_trace_rays_batch(M, a, r_obs, alpha, theta, th_obs, refine)
     same_seq = (steps == steps_o).all(axis=1)
-    # 1-ulp sensitivity of the reference's own result
+    # 1-ulp sensitivity of the reference's own result: to the input angle, and to its libm (every
+    # sin/cos(theta) of the right-hand side moved by one ulp — what a different libm, or CUDA's
+    # math library, does in a few percent of the calls)
     spread = np.zeros(alpha.size)
     flip_ok = np.zeros(alpha.size, dtype=bool)
-    for sh in (np.nextafter(alpha, np.inf), np.nextafter(alpha, -np.inf)):
-        fa_p, w_p, st_p, _ = oracle.kerr_trace_rays_batch(M, a, r_obs, sh, theta, th_obs, refine)
+    probes = [oracle.kerr_trace_rays_batch(M, a, r_obs, sh, theta, th_obs, refine)
+              for sh in (np.nextafter(alpha, np.inf), np.nextafter(alpha, -np.inf))]
+    probes += [oracle.kerr_trace_rays_batch(M, a, r_obs, alpha, theta, th_obs, refine, trig_shift=k)
+               for k in (1, 2, 3, 4, 5, 6)]
+    for fa_p, w_p, st_p, steps_p in probes:
         both = np.isfinite(fa_p) & np.isfinite(fa_o)
         spread[both] = np.fmax(spread[both], np.abs(fa_p[both] - fa_o[both]) / np.maximum(fa_o[both], 1e-3))
         flip_ok |= (st_p != st_o) | (w_p != w_o)
@@ -45,7 +52,7 @@ def _check(oracle, M, a, r_obs, th_obs, alpha, theta, refine, fa, w, st, steps, 
     rel[esc] = np.abs(fa[esc] - fa_o[esc]) / np.maximum(fa_o[esc], 1e-3)
     quantum = np.zeros(alpha.size)
     quantum[esc] = 2.0 ** -52 / np.maximum(np.sin(fa_o[esc]), 1e-300) / np.maximum(fa_o[esc], 1e-3)
-    bad = esc & (rel > REL_TOL + 2 * spread + 2 * quantum)
+    bad = esc & (rel > REL_TOL + 3 * spread + 2 * quantum)
     n_flip = int((~same_seq).sum())
     print("%s: %d rays, %d escaped compared, worst rel err %.2e; %d with a different accept/reject sequence "
           "(their worst rel err %.2e); %d rays with 1-ulp sensitivity > 1e-10"
