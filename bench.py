@@ -267,12 +267,23 @@ def run_gpu(args):
     # source image goes pinned host -> device, the fused kernel renders this rank's tile, the
     # tile goes device -> pinned host; two streams, so one frame's H2D overlaps the previous
     # frame's D2H.  Timed as K frames between two events on the current stream.
-    host_pipe = il.HostFramePipeline((H, W, 3), torch.float32, VFOV_DEG, metric, depth=2)
+    # N > 1 (dist.ShardedHostFrames): every rank uploads only ITS rows of the source over its own
+    # PCIe link and an NCCL all-gather over NVLink replicates the source on every GPU.
     tile_hosts = [tile_host, torch.empty((rows, W, 3), dtype=torch.float32).pin_memory()]
+    if N == 1:
+        host_pipe = il.HostFramePipeline((H, W, 3), torch.float32, VFOV_DEG, metric, depth=2)
+
+        def submit(j):
+            host_pipe.submit(src_host, R_OBS, out=tile_hosts[j % 2], rows=(row0, rows), fov=fov)
+    else:
+        host_pipe = lpdist.ShardedHostFrames((H, W, 3), torch.float32, metric=metric, depth=2)
+
+        def submit(j):
+            host_pipe.submit(src_host, fov, R_OBS, out=tile_hosts[j % 2])
 
     def run_e2e(k):
         for j in range(k):
-            host_pipe.submit(src_host, R_OBS, out=tile_hosts[j % 2], rows=(row0, rows), fov=fov)
+            submit(j)
         host_pipe.synchronize()
 
     def timed_e2e(k):
@@ -281,7 +292,7 @@ def run_gpu(args):
         barrier()
         a.record()
         for j in range(k):
-            host_pipe.submit(src_host, R_OBS, out=tile_hosts[j % 2], rows=(row0, rows), fov=fov)
+            submit(j)
         for slot in host_pipe._slots:
             torch.cuda.current_stream().wait_stream(slot["stream"])
         b.record()
@@ -428,10 +439,14 @@ def run_gpu(args):
             "config": workload_config(N, H, W, gather_mode),
             "ms_per_frame": total_ms / args.steps,
             "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_frame": total_e2e / args.steps,
-                    "h2d_bytes_per_step": int(src_host.numel() * 4 * N),
+                    "h2d_bytes_per_step": int(src_host.numel() * 4),
                     "d2h_bytes_per_step": int(rays * 12),
-                    "path": "image_lens.HostFramePipeline: pinned float32 source -> H2D -> lp_render_frame -> D2H "
-                            "pinned float32 frame, every frame; 2 streams (frame k+1's H2D overlaps frame k's D2H)"},
+                    "path": ("image_lens.HostFramePipeline: pinned float32 source -> H2D -> lp_render_frame -> D2H "
+                             "pinned float32 frame, every frame; 2 streams (frame k+1's H2D overlaps frame k's D2H)")
+                    if N == 1 else
+                            ("dist.ShardedHostFrames: every rank uploads its 1/N of the pinned float32 source, NCCL "
+                             "all-gather replicates it over NVLink, lp_render_frame renders the rank's tile, D2H of "
+                             "the tile to pinned memory, every frame; 2 streams")},
             "gpu_launches": args.steps * (len(bg.bands) if bg is not None else 1),
             "gather": gather_mode,
             "roofline": {"bound": "fp64", "kernel": "lp_render_kernel (alpha + Binet RK4 + remap, fused)",

@@ -161,6 +161,69 @@ class PeerFrame:
         return self.buf if self.rank == self.dst else None
 
 
+class ShardedHostFrames:
+    """Host image in -> this rank's row tile of the lensed frame out, for streams of frames, with
+    the upload SHARDED: every rank copies only its own 1/N of the rows of the source image over
+    its own PCIe link, one NCCL all-gather over NVLink assembles the replicated source on every
+    GPU (the remap may sample any source pixel), the fused kernel renders the rank's tile, the
+    tile goes back to (pinned) host memory.  PCIe carries 1/N of the source per GPU instead of
+    all of it; two slots on two streams overlap one frame's upload with the previous frame's
+    download, as image_lens.HostFramePipeline does on one GPU.  Needs equal row tiles."""
+
+    def __init__(self, shape, dtype, vertical_fov=None, metric=None, depth=2, group=None):
+        import torch
+        import torch.distributed as dist
+        from .metrics import Schwarzschild
+        self.dist, self.group = dist, group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.shape = tuple(shape)
+        self.height, self.width = self.shape[0], self.shape[1]
+        tiles = row_tiles(self.height, self.world)
+        if any(r != tiles[0][1] for _, r in tiles):
+            raise ValueError("ShardedHostFrames needs equal row tiles")
+        self.rows = tiles[self.rank]
+        self.metric = metric if metric is not None else Schwarzschild(M=1.0)
+        self.fov = vertical_fov
+        device = torch.device("cuda", torch.cuda.current_device())
+        tile_shape = (self.rows[1],) + self.shape[1:]
+        self._slots = [dict(stream=torch.cuda.Stream(device=device),
+                            part=torch.empty(tile_shape, dtype=dtype, device=device),
+                            src=torch.empty(self.shape, dtype=dtype, device=device),
+                            frame=torch.empty(tile_shape, dtype=dtype, device=device))
+                       for _ in range(max(1, int(depth)))]
+        self._k = 0
+        self._torch = torch
+
+    def submit(self, host_src, fov, r_obs, psi=(0.0, 0.0), out=None, flags=None):
+        """host_src: the full [H, W, ...] pinned host image (only this rank's rows are read).
+        Returns the pinned host tensor that holds this rank's tile after synchronize()."""
+        from . import image_lens as il
+        from . import _device as dev
+        t = self._torch
+        slot = self._slots[self._k % len(self._slots)]
+        self._k += 1
+        row0, n = self.rows
+        if out is None:
+            out = t.empty((n,) + self.shape[1:], dtype=slot["src"].dtype).pin_memory()
+        st = slot["stream"]
+        st.wait_stream(t.cuda.current_stream())
+        with t.cuda.stream(st):
+            slot["part"].copy_(host_src[row0:row0 + n], non_blocking=True)
+            self.dist.all_gather_into_tensor(slot["src"].view(self.world, -1), slot["part"].view(-1),
+                                             group=self.group)
+            il.render_frame(slot["src"], fov, r_obs, self.metric, psi=psi, rows=(row0, n),
+                            flags=dev.TRACE_HYBRID if flags is None else flags, out=slot["frame"])
+            out.copy_(slot["frame"], non_blocking=True)
+        return out
+
+    def synchronize(self):
+        cur = self._torch.cuda.current_stream()
+        for slot in self._slots:
+            cur.wait_stream(slot["stream"])
+        cur.synchronize()
+
+
 class RowShardedRenderer:
     """Row-tile sharded lensed render (BASELINE config 4): each rank renders its tile with the
     fused kernel, then the frame is gathered over NCCL / NVLink."""
