@@ -47,6 +47,13 @@ def _worker(rank, world, port, q):
                    "peer": (bool(torch.equal(c, full)) if peer_ok is True else peer_ok)}
         every = rs.render(30.0, psi=(0.05, -0.02), dst=None)      # all_gather: every rank gets the frame
         res["all"] = bool(torch.equal(every, full))
+        # host image in / host tile out with the upload sharded over the ranks
+        pipe = lpdist.ShardedHostFrames((H, W, 3), torch.float32, metric=metric, depth=2)
+        host_src = src.cpu().pin_memory()
+        outs = [pipe.submit(host_src, rs.pipe.fov, 30.0, psi=(0.05, -0.02)) for _ in range(3)]
+        pipe.synchronize()
+        r0, n = pipe.rows
+        res["sharded_host"] = all(bool(torch.equal(o, full[r0:r0 + n].cpu())) for o in outs)
         q.put((rank, res))
     finally:
         dist.destroy_process_group()
@@ -68,4 +75,5 @@ def test_two_rank_frame_bit_identical(native):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert results[0]["gather"] and results[0]["bands"] and results[0]["all"] and results[1]["all"]
+    assert results[0]["sharded_host"] and results[1]["sharded_host"]
     assert results[0]["peer"] is True, results[0]["peer"]
