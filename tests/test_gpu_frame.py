@@ -378,3 +378,21 @@ def test_frame_4k_vs_oracle(native, oracle):
     bad = (np.abs(np.floor(fused * 255) - np.floor(ref * 255)) > 1).any(-1)
     print("4K fused frame: %d pixels differ by more than 1/255 from the reference pipeline" % int(bad.sum()))
     assert bad.sum() <= 16
+
+
+def test_capture_sweep_graph(native):
+    """LensPipeline.capture_sweep: the CUDA-graph replay of a sweep writes the frames the
+    one-by-one renders write (and again after the buffers were cleared)."""
+    import torch
+    il = _il()
+    metric = _metric(1.0)
+    src = torch.rand(96, 128, 3, device="cuda")
+    pipe = il.LensPipeline(src, 30.0, metric)
+    params = [(15.0, (0.0, 0.0)), (40.0, (0.05, 0.0)), (100.0, (0.0, -0.1)), (600.0, (-0.1, 0.1))]
+    ref = torch.stack([pipe.render(r, psi=p) for r, p in params])
+    out = torch.empty_like(ref)
+    graph = pipe.capture_sweep(params, out)
+    out.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)

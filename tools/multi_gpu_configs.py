@@ -103,9 +103,16 @@ def sweep():
 
 
 ms = timed(sweep, 3)
+check = frames[-1].clone()
+graph = pipe.capture_sweep([grid[k] for k in mine], frames)
+ms_graph = timed(graph.replay, 3)
+same = bool(torch.equal(check, frames[-1]))
 if rank == 0:
     print(json.dumps({"config": "5: %d-frame sweep 1024x1024, frame-sharded x%d" % (len(grid), world),
                       "ms_total": ms, "ms_per_frame": ms / len(grid), "frames_per_s": len(grid) / ms * 1e3,
-                      "rays_per_s": len(grid) * Hs * Ws / ms * 1e3}), flush=True)
+                      "rays_per_s": len(grid) * Hs * Ws / ms * 1e3,
+                      "cuda_graph": {"ms_total": ms_graph, "ms_per_frame": ms_graph / len(grid),
+                                     "rays_per_s": len(grid) * Hs * Ws / ms_graph * 1e3,
+                                     "same_frames": same}}), flush=True)
 if world > 1:
     dist.destroy_process_group()
