@@ -164,7 +164,7 @@ def workload_config(n, H, W, gather_mode="nccl"):
                              "each tile rendered in bands whose NCCL gather to rank 0 overlaps the next band's render"))
             if n > 1 else "single GPU",
             "arithmetic": "hybrid (LP_TRACE_HYBRID, the image pipeline's default): FMA-contracted RK4 loop, strict "
-                          "re-trace of rays longer than 192 steps; same classification / winding / float32 "
+                          "re-trace of rays longer than 240 steps; same classification / winding / float32 "
                           "final_alpha as the strict kernel on this frame (tests/test_gpu_frame.py)",
             "l2": "256 MiB buffer written between timed steps (L2 flush)"}
 

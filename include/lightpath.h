@@ -46,9 +46,9 @@ extern "C" {
 #define LP_TRACE_FUSED      1u    /* allow FMA contraction inside the RK4 step
                                      (faster, ulp-level different trajectories)     */
 #define LP_TRACE_NO_REPACK  2u    /* reserved                                        */
-#define LP_TRACE_HYBRID     4u    /* FMA-contracted loop for rays that finish within 9.6 rad
-                                     of swept angle (192 RK4 steps at h = 0.05; they stay
-                                     within 1e-12 of the strict result), strict re-trace of
+#define LP_TRACE_HYBRID     4u    /* FMA-contracted loop for rays that finish within 12 rad
+                                     of swept angle (240 RK4 steps at h = 0.05; they stay
+                                     within 1e-11 of the strict result), strict re-trace of
                                      the few longer ones
                                      (near-critical rays, where rounding differences are
                                      amplified): same classification and winding as

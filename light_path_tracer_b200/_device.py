@@ -13,7 +13,7 @@ H_MAX = 0.05     # metrics.py:833 (and :824 for the scalar path)
 TRACE_STRICT = 0
 TRACE_FUSED = 1
 RENDER_STAGED_STORES = 8   # lp_render_frame: 16-byte staged pixel stores (peer-memory tiles)
-TRACE_HYBRID = 4   # FMA loop + strict re-trace of rays longer than 192 steps (lightpath.h)
+TRACE_HYBRID = 4   # FMA loop + strict re-trace of rays longer than 240 steps (lightpath.h)
 
 _pinned = {}
 

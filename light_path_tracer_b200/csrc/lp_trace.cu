@@ -35,12 +35,12 @@ struct TraceArgs {
 // per operation; the difference grows like e^phi while a ray lingers at the photon sphere.
 // Measured (tools/fma_study.c, 2.4e7 rays over r_obs = 15..1000, dense around alpha_crit):
 // rays that finish within 275 steps agree with the strict loop to <= 3e-11 relative in
-// final_alpha with identical status and n_half_orbits; 192 (phi <= 9.6, <= 1e-12) leaves two
+// final_alpha with identical status and n_half_orbits; 240 (phi <= 12, <= 6e-12) leaves two
 // orders of margin to the 1e-9 parity bound, and in a 4K frame only ~1e-4 of the rays are
 // longer than that (they are the ones the strict retrace exists for).
-// (what matters is the swept angle, 192 steps x 0.05 rad = 9.6 rad: for another step size the
+// (what matters is the swept angle, 240 steps x 0.05 rad = 12 rad: for another step size the
 // threshold is the number of steps that sweeps the same angle)
-#define LP_HYBRID_RETRACE_PHI 9.6
+#define LP_HYBRID_RETRACE_PHI 12.0
 
 static int retrace_steps_for(uint32_t flags, double h_max)
 {
