@@ -79,7 +79,7 @@ lp_trace_kernel(const TraceArgs a, const BinetConsts c, const CamConsts cam)
             if (a.out_alpha32) a.out_alpha32[i] = a32;
             alpha = (double)a32;
         }
-        binet_trace<FUSED, FAST>(c, L, alpha, r);
+        binet_trace<FUSED, FAST, (FUSED && FAST) ? LP_RENDER_DEFAULT_TRIP : 2>(c, L, alpha, r);
         if (FUSED && r.steps > a.retrace_steps) binet_trace<false, FAST>(c, L, alpha, r);
         const double fa = (r.status == 1) ? r.fa : __longlong_as_double(0x7ff8000000000000LL);
         if (WIDE) {

@@ -202,29 +202,39 @@ def trace_rays(metric, r_obs, alphas, lambda_max=1000.0, r_stop_inner=None, r_st
     return tuple(x.cpu().numpy() for x in out)
 
 
+def draw_black_hole(ax, metric, photon_sphere_label='Photon sphere'):
+    """Filled capture radius and (when the metric has one) the photon sphere, as the reference's
+    two plotting scripts draw them (geodesic_tracer.py:104-113, main.py:38-47)."""
+    ring = np.linspace(0, 2 * np.pi, 200)
+    unit = np.stack([np.cos(ring), np.sin(ring)])
+    ax.fill(*(metric.capture_radius() * unit), 'k', label='Event horizon')
+    r_ph = getattr(metric, 'R_PHOTON', None)
+    if r_ph is not None:
+        ax.plot(*(r_ph * unit), 'r--', linewidth=1.5, label=photon_sphere_label)
+
+
+def draw_path(ax, solution, outcome, linewidth=1.2, label=None, dashed_if_captured=True):
+    """One trajectory in the orbital plane: x = r cos(phi), y = r sin(phi) from solution.y[1], [3]."""
+    r, phi = solution.y[1], solution.y[3]
+    escaped = outcome == 'escaped'
+    ax.plot(r * np.cos(phi), r * np.sin(phi), color='steelblue' if escaped else 'crimson',
+            linestyle='-' if (escaped or not dashed_if_captured) else '--', linewidth=linewidth, label=label)
+
+
 def plot_trajectories(metric, r_obs, angles_deg, ax=None):
-    """Plot photon trajectories for several viewing angles (geodesic_tracer.py:89-142); the
-    rays are traced in one launch.  Needs matplotlib (drawing only)."""
+    """Plot photon trajectories for several viewing angles (geodesic_tracer.py:89-142); all rays are
+    traced in one launch (trace_paths).  Needs matplotlib (drawing only)."""
     import matplotlib.pyplot as plt
     if ax is None:
         _, ax = plt.subplots(figsize=(10, 10))
-    theta = np.linspace(0, 2 * np.pi, 200)
-    r_horizon = metric.capture_radius()
-    ax.fill(r_horizon * np.cos(theta), r_horizon * np.sin(theta), 'k', label='Event horizon')
-    if hasattr(metric, 'R_PHOTON'):
-        ax.plot(metric.R_PHOTON * np.cos(theta), metric.R_PHOTON * np.sin(theta), 'r--', linewidth=1.5,
-                label='Photon sphere')
+    draw_black_hole(ax, metric)
     ax.plot(r_obs, 0, 'go', markersize=10, label=f'Observer (r={r_obs}M)')
-    for alpha_deg, (solution, outcome) in zip(angles_deg, trace_paths(metric, r_obs, np.radians(angles_deg))):
-        if solution is None:
-            continue
-        r, phi = solution.y[1], solution.y[3]
-        escaped = outcome == 'escaped'
-        ax.plot(r * np.cos(phi), r * np.sin(phi), color='steelblue' if escaped else 'crimson',
-                linestyle='-' if escaped else '--', linewidth=1.2, label=f'α={alpha_deg}° ({outcome})')
+    traced = trace_paths(metric, r_obs, np.radians(angles_deg))
+    for alpha_deg, (solution, outcome) in zip(angles_deg, traced):
+        if solution is not None:
+            draw_path(ax, solution, outcome, label=f'α={alpha_deg}° ({outcome})')
     ax.set_title(f'Photon trajectories (critical angle ≈ {np.degrees(metric.alpha_crit(r_obs)):.2f}°)')
-    ax.set_xlabel('x / M')
-    ax.set_ylabel('y / M')
+    ax.set(xlabel='x / M', ylabel='y / M')
     ax.set_aspect('equal')
     ax.legend(loc='upper left', fontsize=8)
     ax.grid(True, alpha=0.3)
