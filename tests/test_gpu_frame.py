@@ -396,3 +396,44 @@ def test_capture_sweep_graph(native):
     graph.replay()
     torch.cuda.synchronize()
     assert torch.equal(out, ref)
+
+
+def test_bilinear_sampling_extension(native, oracle, golden):
+    """LP_SAMPLE_BILINEAR (opt-in; the reference samples nearest): same in/out-of-frame decision as
+    nearest (taken from the rounded coordinate), 4-tap blend around the continuous source
+    coordinate with clamped taps.  Checked against a numpy evaluation of the same definition built
+    on the oracle's geometry; nearest pixels that are magenta / winding / black stay so."""
+    il = _il()
+    g = golden("frames_small.npz")
+    meta = golden("golden_meta.json")["frames"]["offset"]
+    H, W = meta["H"], meta["W"]
+    fov, psi = (meta["hfov"], meta["vfov"]), tuple(meta["psi"])
+    fa, w = g["offset_fa32"], g["offset_w16"]
+    yy, xx = np.mgrid[0:H, 0:W]
+    src = np.stack([np.sin(xx / 7.0) * 0.5 + 0.5, np.cos(yy / 5.0) * 0.5 + 0.5, (xx + yy) / (H + W)], -1).astype(np.float32)
+    near, sy_map, sx_map = oracle.render_lensed_image(src, fa, w, fov, False, psi, return_index=True)
+    out = il.render_lensed_image(src, None, fa, w, 0.0, fov, False, psi, sampling=il.SAMPLE_BILINEAR)
+    sampled = sy_map >= 0
+    assert np.array_equal(out[~sampled], near[~sampled])            # captured / winding / magenta untouched
+    # continuous source coordinates, as the oracle forms them (image_lens.py:310-375)
+    fx, fy = oracle.focal((H, W), fov)
+    d, e_x, e_y, _ = oracle.psi_frame(psi)
+    xc = (np.arange(W) - W / 2) / fx
+    yc = (np.arange(H) - H / 2) / fy
+    norm = np.sqrt(1.0 + xc[None, :] ** 2 + yc[:, None] ** 2)
+    vx, vy, vz = xc[None, :] / norm, yc[:, None] / norm, 1.0 / norm
+    th = np.arctan2(vx * e_x[0] + vy * e_x[1] + vz * e_x[2], vx * e_y[0] + vy * e_y[1] + vz * e_y[2])
+    f = fa.astype(np.float64)
+    with np.errstate(invalid="ignore"):
+        s = [np.cos(f) * d[k] + np.sin(f) * (np.sin(th) * e_x[k] + np.cos(th) * e_y[k]) for k in range(3)]
+        px = s[0] / s[2] * fx + W / 2
+        py = s[1] / s[2] * fy + H / 2
+    x0 = np.floor(px[sampled]); y0 = np.floor(py[sampled])
+    tx = (px[sampled] - x0)[:, None]; ty = (py[sampled] - y0)[:, None]
+    cl = lambda v, n: np.clip(v.astype(np.int64), 0, n - 1)
+    X0, X1, Y0, Y1 = cl(x0, W), cl(x0 + 1, W), cl(y0, H), cl(y0 + 1, H)
+    srcd = src.astype(np.float64)
+    ref = ((1 - tx) * (1 - ty) * srcd[Y0, X0] + tx * (1 - ty) * srcd[Y0, X1]
+           + (1 - tx) * ty * srcd[Y1, X0] + tx * ty * srcd[Y1, X1])
+    assert np.abs(out[sampled] - ref).max() <= 2e-6
+    assert np.abs(out[sampled] - near[sampled]).max() > 1e-3        # it really interpolates
