@@ -301,3 +301,33 @@ def test_small_final_alpha_einstein_ring(native, oracle):
     # of an ulp of that, so a handful of rays may sit on a rounding boundary: allow 0.1 %
     assert (rel > REL_TOL).mean() <= 1e-3
     assert rel.max() <= 1e-6
+
+
+@pytest.mark.parametrize("phi_max,h_max", [(0.3, 0.05), (1.0, 0.05), (7.03, 0.05), (50.0, 0.2), (3.14, 0.013), (50.0, 0.05)])
+def test_hybrid_odd_step_budgets(native, oracle, phi_max, h_max):
+    """The C ABI takes phi_max / h_max (the reference hard-codes 50.0 / 0.05 only in the batch API):
+    hybrid arithmetic with step budgets that are not multiples of the 4-step trip, with shortened
+    last steps, and with other step sizes (the re-trace threshold follows the swept angle) —
+    against the oracle: status via NaN pattern, winding exact, final_alpha within the bar."""
+    import torch
+    from light_path_tracer_b200 import _lib
+    e = _lib.ext()
+    rng = np.random.default_rng(31)
+    M, r_obs = 1.0, 30.0
+    ac = float(oracle.alpha_crit(M, r_obs))
+    alpha = np.concatenate([rng.uniform(0, np.pi, 20000), ac * (1 + rng.normal(0, 1e-3, 10000)), rng.uniform(0, 2 * ac, 10000)])
+    fa_o, w_o, st_o, steps_o = oracle.trace_rays_batch(M, r_obs, alpha, phi_max=phi_max, h_max=h_max)
+    d_a = torch.from_numpy(alpha).cuda()
+    for flags in (0, 4):
+        fa = torch.empty(alpha.size, dtype=torch.float64, device="cuda")
+        w = torch.empty(alpha.size, dtype=torch.int64, device="cuda")
+        steps = torch.empty(alpha.size, dtype=torch.int32, device="cuda")
+        e.trace_batch_f64(d_a, M, 2 * M, r_obs, phi_max, h_max, fa, w, None, steps, None, flags)
+        fa, w = fa.cpu().numpy(), w.cpu().numpy()
+        assert np.array_equal(np.isnan(fa), np.isnan(fa_o)), (flags, int((np.isnan(fa) != np.isnan(fa_o)).sum()))
+        assert np.array_equal(w, w_o)
+        ok = np.isfinite(fa_o)
+        rel = np.abs(fa[ok] - fa_o[ok]) / np.maximum(fa_o[ok], FA_FLOOR)
+        assert rel.max() <= REL_TOL, (flags, rel.max())
+        if flags == 0:
+            assert (steps.cpu().numpy() != steps_o).mean() < 0.01
