@@ -223,7 +223,7 @@ def test_fused_mode_within_tolerance(native, oracle):
     _check_batch(1.0, 100.0, alpha, fa_o, w_o, d_fa.cpu().numpy(), d_w.cpu().numpy(), "fused", oracle)
 
 
-@pytest.mark.parametrize("r_obs", [15.0, 100.0, 1000.0])
+@pytest.mark.parametrize("r_obs", [15.0, 100.0, 1000.0, 3.0, 2.3])
 def test_hybrid_mode_matches_strict(native, oracle, r_obs):
     """LP_TRACE_HYBRID = FMA-contracted loop, strict re-trace of every ray longer than 240
     steps.  Against the strict kernel on the same device: status and n_half_orbits identical
@@ -261,9 +261,10 @@ def test_hybrid_mode_matches_strict(native, oracle, r_obs):
     rel = np.maximum(np.abs(fa_h[esc] - fa_s[esc]) - 2 * quantum, 0.0) / np.maximum(fa_s[esc], 1e-3)
     long_rays = n_h > 240
     assert bits_equal(fa_s[long_rays], fa_h[long_rays]) and np.array_equal(n_s[long_rays], n_h[long_rays])
+    worst = float(rel.max()) if rel.size else 0.0        # inside the photon sphere every ray is captured
     print("r_obs=%g: %d rays, %d escaped, %d re-traced (>240 steps), max rel diff %.2e" % (
-        r_obs, alpha.size, int(esc.sum()), int(long_rays.sum()), float(rel.max())))
-    assert rel.max() <= REL_TOL
+        r_obs, alpha.size, int(esc.sum()), int(long_rays.sum()), worst))
+    assert worst <= REL_TOL
 
 
 def test_small_final_alpha_einstein_ring(native, oracle):
