@@ -409,6 +409,12 @@ def run_gpu(args):
                                             "frac_of_measured_fp64_peak": flops_tile / t_fused / 1e9 / peak_tf},
             "remap_kernel": {"ms": t_remap, "gb_per_s": H * W * 30 / t_remap / 1e6, "bytes_per_px": 30,
                              "frac_of_measured_hbm": H * W * 30 / t_remap / 1e6 / hbm_peak()},
+            # kernel (2) in the shape of the `roofline` object (its bound is HBM)
+            "roofline_remap": {"bound": "hbm", "kernel": "lp_remap_f32rgb_x4_kernel (stand-alone remap)",
+                               "achieved": H * W * 30 / t_remap / 1e6, "peak": hbm_peak(), "unit": "GB/s",
+                               "frac": H * W * 30 / t_remap / 1e6 / hbm_peak(),
+                               "traffic": ncu_traffic("lp_remap_f32rgb_x4_kernel"),
+                               "peak_source": "MEASURED_PEAKS.json hbm_gbs (6650 fallback)"},
         }
 
     # max over ranks, on the device
@@ -484,11 +490,11 @@ def hbm_peak():
         return 6650.0     # B200_PROFILING.md fallback
 
 
-def ncu_traffic():
-    """dram bytes per launch of the fused kernel from the committed ncu capture, if any."""
+def ncu_traffic(kernel="lp_render_kernel"):
+    """dram bytes per launch of a kernel from the committed ncu capture, if any."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
-            return json.load(f).get("lp_render_kernel", {}).get("dram_bytes_per_launch")
+            return json.load(f).get(kernel, {}).get("dram_bytes_per_launch")
     except Exception:
         return None
 
