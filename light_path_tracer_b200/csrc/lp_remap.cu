@@ -7,6 +7,7 @@
 // neighbouring source texels (L1/L2 resident).  All direction math is fp64 like the
 // reference's; what must match is the INTEGER source index.
 #include "lp_remap.cuh"
+#include <stdlib.h>
 
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -31,6 +32,7 @@ lp_remap_kernel(const RemapArgs a, const CamConsts cam)
 // the one-pixel-per-thread kernel (the remap is latency-, not bandwidth-limited otherwise).
 // Same per-pixel decisions as remap_pixel(), same integer source index.
 #define LP_REMAP4_BLOCK 128
+#define LP_REMAP4_DEFAULT_MINB 12
 
 // sin and cos on [0, pi/2] (final_alpha of a sampled pixel is a float32 in that range): one
 // conditional reflection about pi/4 instead of a general quadrant reduction, the fdlibm kernel
@@ -53,7 +55,8 @@ __device__ __forceinline__ void sincos_first_quadrant(double x, double &s, doubl
     c = hi ? sr : cr;
 }
 
-__global__ void __launch_bounds__(LP_REMAP4_BLOCK)
+template <int MINB>
+__global__ void __launch_bounds__(LP_REMAP4_BLOCK, MINB)
 lp_remap_f32rgb_x4_kernel(const RemapArgs a, const CamConsts cam)
 {
     const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -161,7 +164,16 @@ extern "C" int lp_remap(const void *src, int32_t src_dtype, int32_t channels,
         const long long quads = a.n / 4;                 // width % 4 == 0 -> n % 4 == 0
         const long long blocks = (quads + LP_REMAP4_BLOCK - 1) / LP_REMAP4_BLOCK;
         if (blocks > 0x7fffffffLL) return LP_ERR_UNSUPPORTED;
-        lp_remap_f32rgb_x4_kernel<<<(unsigned)blocks, LP_REMAP4_BLOCK, 0, st>>>(a, cam);
+        static int minb = 0;                              // LP_REMAP_MINB: register-cap tuning knob
+        if (!minb) {
+            const char *e = getenv("LP_REMAP_MINB");
+            const int v = e ? atoi(e) : 0;
+            minb = (v == 6 || v == 8 || v == 10 || v == 12) ? v : LP_REMAP4_DEFAULT_MINB;
+        }
+        if (minb == 6) lp_remap_f32rgb_x4_kernel<6><<<(unsigned)blocks, LP_REMAP4_BLOCK, 0, st>>>(a, cam);
+        else if (minb == 10) lp_remap_f32rgb_x4_kernel<10><<<(unsigned)blocks, LP_REMAP4_BLOCK, 0, st>>>(a, cam);
+        else if (minb == 12) lp_remap_f32rgb_x4_kernel<12><<<(unsigned)blocks, LP_REMAP4_BLOCK, 0, st>>>(a, cam);
+        else lp_remap_f32rgb_x4_kernel<8><<<(unsigned)blocks, LP_REMAP4_BLOCK, 0, st>>>(a, cam);
         return lp_check_launch();
     }
     const void *fn;
