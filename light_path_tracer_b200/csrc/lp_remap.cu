@@ -32,7 +32,7 @@ lp_remap_kernel(const RemapArgs a, const CamConsts cam)
 // the one-pixel-per-thread kernel (the remap is latency-, not bandwidth-limited otherwise).
 // Same per-pixel decisions as remap_pixel(), same integer source index.
 #define LP_REMAP4_BLOCK 128
-#define LP_REMAP4_DEFAULT_MINB 12
+#define LP_REMAP4_DEFAULT_QUADS 1
 
 // sin and cos on [0, pi/2] (final_alpha of a sampled pixel is a float32 in that range): one
 // conditional reflection about pi/4 instead of a general quadrant reduction, the fdlibm kernel
@@ -55,26 +55,13 @@ __device__ __forceinline__ void sincos_first_quadrant(double x, double &s, doubl
     c = hi ? sr : cr;
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(LP_REMAP4_BLOCK, MINB)
-lp_remap_f32rgb_x4_kernel(const RemapArgs a, const CamConsts cam)
+// The per-quad pieces of the fast path: decisions + source offsets (pure math), gather, store.
+__device__ __forceinline__ void quad_offsets(const RemapArgs &a, const CamConsts &cam, int col, double Ay, double By,
+                                             const float4 fa4, const ushort4 w4, float (&o)[12], int (&off)[4])
 {
-    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (i >= a.n) return;
-    int row, col;
-    pixel_row_col(i, a.n, cam.width, a.row0, row, col);
-    const float4 fa4 = __ldg(reinterpret_cast<const float4 *>(a.fa32 + i));
-    ushort4 w4 = make_ushort4(0, 0, 0, 0);
-    if (a.w16) w4 = __ldg(reinterpret_cast<const ushort4 *>(a.w16 + i));
     const float fa[4] = {fa4.x, fa4.y, fa4.z, fa4.w};
     const unsigned wn[4] = {w4.x, w4.y, w4.z, w4.w};
-    const float *__restrict__ src = (const float *)a.src;
     const int H = cam.height, W = cam.width;                 // the host checks H * W * 3 < 2^31 for this kernel
-    float o[12];
-    int off[4];
-    // row-constant parts of the two dot products A = v.e_x, B = v.e_y (v = (x_cam, y_cam, 1))
-    const double yc = cam_y(cam, row);
-    const double Ay = fma(yc, cam.ex1, cam.ex2), By = fma(yc, cam.ey1, cam.ey2);
     double px[4], py[4];
     bool front[4];
 #pragma unroll
@@ -123,6 +110,10 @@ lp_remap_f32rgb_x4_kernel(const RemapArgs a, const CamConsts cam)
             else { o[3 * p] = 1.0f; o[3 * p + 1] = 0.0f; o[3 * p + 2] = 1.0f; }
         }
     }
+}
+
+__device__ __forceinline__ void quad_gather(const float *__restrict__ src, const int (&off)[4], float (&o)[12])
+{
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
         if (off[p] >= 0) {
@@ -131,10 +122,47 @@ lp_remap_f32rgb_x4_kernel(const RemapArgs a, const CamConsts cam)
             o[3 * p + 2] = __ldg(src + off[p] + 2);
         }
     }
-    float4 *dst = reinterpret_cast<float4 *>((float *)a.out + i * 3);
+}
+
+__device__ __forceinline__ void quad_store(float *out, long long i, const float (&o)[12])
+{
+    float4 *dst = reinterpret_cast<float4 *>(out + i * 3);
     dst[0] = make_float4(o[0], o[1], o[2], o[3]);
     dst[1] = make_float4(o[4], o[5], o[6], o[7]);
     dst[2] = make_float4(o[8], o[9], o[10], o[11]);
+}
+
+// QUADS consecutive quads per thread, software-pipelined: all lookups are loaded up front, the
+// gathers of quad q are issued before the math of quad q+1 starts (so they are in flight under
+// it), all stores come last.
+template <int MINB, int QUADS>
+__global__ void __launch_bounds__(LP_REMAP4_BLOCK, MINB)
+lp_remap_f32rgb_x4_kernel(const RemapArgs a, const CamConsts cam)
+{
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * (4 * QUADS);
+    if (i >= a.n) return;
+    int row, col;
+    pixel_row_col(i, a.n, cam.width, a.row0, row, col);
+    float4 fa4[QUADS];
+    ushort4 w4[QUADS];
+#pragma unroll
+    for (int q = 0; q < QUADS; ++q) {
+        fa4[q] = __ldg(reinterpret_cast<const float4 *>(a.fa32 + i) + q);
+        w4[q] = a.w16 ? __ldg(reinterpret_cast<const ushort4 *>(a.w16 + i) + q) : make_ushort4(0, 0, 0, 0);
+    }
+    const float *__restrict__ src = (const float *)a.src;
+    // row-constant parts of the two dot products A = v.e_x, B = v.e_y (v = (x_cam, y_cam, 1))
+    const double yc = cam_y(cam, row);
+    const double Ay = fma(yc, cam.ex1, cam.ex2), By = fma(yc, cam.ey1, cam.ey2);
+    float o[QUADS][12];
+    int off[QUADS][4];
+#pragma unroll
+    for (int q = 0; q < QUADS; ++q) {
+        quad_offsets(a, cam, col + 4 * q, Ay, By, fa4[q], w4[q], o[q], off[q]);
+        quad_gather(src, off[q], o[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < QUADS; ++q) quad_store((float *)a.out, i + 4 * q, o[q]);
 }
 
 extern "C" int lp_remap(const void *src, int32_t src_dtype, int32_t channels,
@@ -164,16 +192,18 @@ extern "C" int lp_remap(const void *src, int32_t src_dtype, int32_t channels,
         const long long quads = a.n / 4;                 // width % 4 == 0 -> n % 4 == 0
         const long long blocks = (quads + LP_REMAP4_BLOCK - 1) / LP_REMAP4_BLOCK;
         if (blocks > 0x7fffffffLL) return LP_ERR_UNSUPPORTED;
-        static int minb = 0;                              // LP_REMAP_MINB: register-cap tuning knob
-        if (!minb) {
-            const char *e = getenv("LP_REMAP_MINB");
+        // LP_REMAP_QUADS = 1 | 2 quads per thread (tuning knob); 2 needs width % 8 == 0
+        static int quads_per_thread = 0;
+        if (!quads_per_thread) {
+            const char *e = getenv("LP_REMAP_QUADS");
             const int v = e ? atoi(e) : 0;
-            minb = (v == 6 || v == 8 || v == 10 || v == 12) ? v : LP_REMAP4_DEFAULT_MINB;
+            quads_per_thread = (v == 1 || v == 2) ? v : LP_REMAP4_DEFAULT_QUADS;
         }
-        if (minb == 6) lp_remap_f32rgb_x4_kernel<6><<<(unsigned)blocks, LP_REMAP4_BLOCK, 0, st>>>(a, cam);
-        else if (minb == 10) lp_remap_f32rgb_x4_kernel<10><<<(unsigned)blocks, LP_REMAP4_BLOCK, 0, st>>>(a, cam);
-        else if (minb == 12) lp_remap_f32rgb_x4_kernel<12><<<(unsigned)blocks, LP_REMAP4_BLOCK, 0, st>>>(a, cam);
-        else lp_remap_f32rgb_x4_kernel<8><<<(unsigned)blocks, LP_REMAP4_BLOCK, 0, st>>>(a, cam);
+        const int qpt = (quads_per_thread == 2 && cam.width % 8 == 0) ? 2 : 1;
+        const long long threads = (quads + qpt - 1) / qpt;
+        const long long nblocks = (threads + LP_REMAP4_BLOCK - 1) / LP_REMAP4_BLOCK;
+        if (qpt == 2) lp_remap_f32rgb_x4_kernel<8, 2><<<(unsigned)nblocks, LP_REMAP4_BLOCK, 0, st>>>(a, cam);
+        else lp_remap_f32rgb_x4_kernel<12, 1><<<(unsigned)nblocks, LP_REMAP4_BLOCK, 0, st>>>(a, cam);
         return lp_check_launch();
     }
     const void *fn;
