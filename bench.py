@@ -124,6 +124,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; this arm is the only work on the box and
+    # must use all the host threads it can, so size the OpenMP pool before libgomp initialises
+    os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
     import lp_oracle as O
     O.build()
     H, W = H0 * args.gpus, W0
