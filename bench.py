@@ -480,6 +480,26 @@ def run_gpu(args):
                 "sample": "one full %dx%d frame (%.1f s): oracle port of the reference's CPU path, trace on %d "
                           "OpenMP threads, alpha lookup / remap single-threaded numpy like the reference"
                           % (W, H, t_cpu, O.num_threads())}
+            # CPU figures beside the two secondary kernels, on a stratified sample of the same frame
+            # (SURVEY.md 8d); the C port has none of scipy's per-call Python cost (15-32 ms/ray there)
+            stride = (H * W) // 32768
+            a_s = O.build_alpha_lookup((H, W), fov).reshape(-1)[::stride].astype(np.float64)
+            t0 = time.perf_counter()
+            O.rk45_trace_batch(M, R_OBS, a_s)
+            t_rk_cpu = time.perf_counter() - t0
+            th_s = il._theta_pixel((H, W), fov, (0.0, 0.0), H).reshape(-1)[::stride]
+            if "config3_rk45_frame_4k" in line:
+                line["config3_rk45_frame_4k"]["cpu_port"] = {
+                    "rays_per_s": a_s.size / t_rk_cpu, "cores": O.num_threads(),
+                    "sample": "every %dth pixel (%d rays), C port of scipy RK45 + events" % (stride, a_s.size)}
+            if "kerr_lookup_4k" in line:
+                t0 = time.perf_counter()
+                O.kerr_trace_rays_batch(M, 0.9, R_OBS, a_s, np.asarray(th_s, np.float64), np.pi / 2)
+                t_k_cpu = time.perf_counter() - t0
+                line["kerr_lookup_4k"]["cpu_port"] = {
+                    "rays_per_s": a_s.size / t_k_cpu, "cores": O.num_threads(),
+                    "sample": "every %dth pixel (%d rays), C restatement of the numba Kerr DP45 tracer"
+                              % (stride, a_s.size)}
         print(json.dumps(line), flush=True)
     if N > 1:
         dist.destroy_process_group()

@@ -6,23 +6,31 @@
 // per-pixel driver precompute_final_alpha_lookup_2d (image_lens.py:185-280).
 //
 // GPU layout: persistent warps, one ray per LANE, every trip of the main loop is one step
-// ATTEMPT (accepted or rejected) for all 32 lanes; a lane whose ray has ended takes the next
-// ray of its warp's queue as soon as >= KERR_REFILL_MIN lanes are idle (ballot + rank), so
-// captured / escaped rays stop occupying lanes (adaptive step counts differ 3x between
-// neighbouring rays near the shadow edge).  State, the seven stage vectors and the controller
-// live in registers, fp64.  No shared memory, no atomics, no hidden state.
+// ATTEMPT (accepted or rejected) for all 32 lanes.  A lane whose ray has ended PARKS with its
+// final state; once >= KERR_REFILL_MIN lanes are parked or empty (ballot) the warp runs one
+// flush phase: final direction + stores for all parked lanes together, then the next rays of
+// the warp's queue are initialised into the free lanes together (ballot + rank).  The divergent
+// per-ray work (extract angle: ~600 instructions, initial conditions + first right-hand side:
+// ~1500) is thereby paid once per ~8 rays instead of once per ray, and captured / escaped rays
+// stop occupying lanes (adaptive step counts differ 3x between neighbouring rays near the
+// shadow edge).  State, the seven stage vectors and the controller live in registers, fp64;
+// the right-hand side is one __noinline__ function (arguments and results in registers) so the
+// hot loop stays inside the instruction cache.  No shared memory, no atomics, no hidden state.
 //
 // Arithmetic: every expression is written in the reference's order and the library is built
 // with -fmad=false, so all +,-,*,/ and sqrt round exactly like the numba build; what differs
 // from the host is the transcendental library (sin/cos of theta in the right-hand side, pow in
-// the controller, arccos at the end), each within 1-2 ulp.  The right-hand side exists in two
-// forms: EXACT (14 IEEE divisions; the default) and a shared-reciprocal form within a few ulp of
-// it (2.7x faster, opt-in, outside the parity bar for axis_refine rays: see kerr_fast_rhs).
+// the controller, arccos at the end), each within 1-2 ulp.  The right-hand side's 14 IEEE
+// divisions share 7 denominators: each quotient is formed as the compiler's own division
+// sequence with the reciprocal part hoisted (div_rcp / div_by, lp_internal.cuh) — bit-identical
+// quotients, 204 instead of 235 FP64-pipe slots and 325 instead of 604 instructions per
+// evaluation.  A second form over three approximate reciprocals (within a few ulp; opt-in,
+// outside the parity bar for axis_refine rays: see kerr_fast_rhs) is kept for comparison.
 #include "lp_internal.cuh"
 #include <stdlib.h>
 
 #define KERR_BLOCK 128
-#define KERR_REFILL_MIN 4
+#define KERR_REFILL_MIN 8
 #define KERR_DEFAULT_MINB 4
 
 struct KerrArgs {
@@ -38,7 +46,7 @@ struct KerrArgs {
     double sin_th_obs, cos_th_obs;   // host libm (the reference's own), one value per launch
     // outputs (WIDE: f64 / i64, else f32 / u16)
     void *out_fa, *out_w;
-    int32_t wide;
+    int32_t wide, refill_min;
     int8_t *out_status;              // optional
     int32_t *out_steps;              // optional [n][2]: accepted steps, attempts
 };
@@ -53,47 +61,58 @@ static __constant__ double kA21 = 1.0 / 5.0, kA31 = 3.0 / 40.0, kA32 = 9.0 / 40.
 
 // metrics.py:227-306.  EXACT: the reference's expression tree with one IEEE division per `/`;
 // otherwise the same expressions over three shared reciprocals (see below).
+struct K5 { double v0, v1, v2, v3, v4; };
+
+// All arguments and the five derivatives travel in registers (scalars by value, a plain struct
+// back): array references to a __noinline__ function would go through local memory.
 template <bool EXACT>
-__device__ __noinline__ void kerr_rhs(const double (&s)[5], double p_t, double p_phi, double M, double a,
-                                      double r_floor, double (&out)[5])
+__device__ __noinline__ K5 kerr_rhs_regs(double r, double th, double p_r, double p_th, double p_t, double p_phi,
+                                         double M, double a, double r_floor)
 {
-    const double r = s[0], th = s[1], p_r = s[3], p_th = s[4];
+    K5 out;
     if (r <= r_floor) {
-#pragma unroll
-        for (int i = 0; i < 5; ++i) out[i] = 0.0;
-        return;
+        out.v0 = out.v1 = out.v2 = out.v3 = out.v4 = 0.0;
+        return out;
     }
     double sin_th, cos_th;
     sincos(th, &sin_th, &cos_th);
     double sin_th_sq = sin_th * sin_th;
     if (sin_th_sq < 1e-15) sin_th_sq = 1e-15;
     if (EXACT) {
+    // The reference's expression tree, one IEEE quotient per `/` (bit for bit: div_by), over the
+    // 7 distinct denominators its 14 divisions share.
     const double Sigma = r * r + a * a * cos_th * cos_th;
     const double Delta = r * r - 2.0 * M * r + a * a;
     const double A = (r * r + a * a) * (r * r + a * a) - a * a * Delta * sin_th_sq;
-    const double g_tphi_inv = -2.0 * M * a * r / (Sigma * Delta);
-    const double g_rr_inv = Delta / Sigma;
-    const double g_thth_inv = 1.0 / Sigma;
-    const double g_phiphi_inv = (Delta - a * a * sin_th_sq) / (Sigma * Delta * sin_th_sq);
+    const double sigma_delta = Sigma * Delta;
+    const double sigma_sq = Sigma * Sigma;
+    const double sigma_sq_delta = sigma_sq * Delta;
+    const double sigma_delta_sq = sigma_delta * sigma_delta;
+    const double den = sigma_delta * sin_th_sq;
+    const double den_sq = den * den;
+    const double y_S = div_rcp(Sigma), y_SD = div_rcp(sigma_delta), y_S2 = div_rcp(sigma_sq);
+    const double y_S2D = div_rcp(sigma_sq_delta), y_SD2 = div_rcp(sigma_delta_sq);
+    const double y_den = div_rcp(den), y_den2 = div_rcp(den_sq);
+    const double g_tphi_inv = div_by(-2.0 * M * a * r, sigma_delta, y_SD);
+    const double g_rr_inv = div_by(Delta, Sigma, y_S);
+    const double g_thth_inv = div_by(1.0, Sigma, y_S);
+    const double g_phiphi_inv = div_by(Delta - a * a * sin_th_sq, den, y_den);
     const double dr = g_rr_inv * p_r;
     const double dth = g_thth_inv * p_th;
     const double dphi = g_tphi_inv * p_t + g_phiphi_inv * p_phi;
     const double dSigma_dr = 2.0 * r;
     const double dDelta_dr = 2.0 * r - 2.0 * M;
     const double dA_dr = 4.0 * r * (r * r + a * a) - a * a * dDelta_dr * sin_th_sq;
-    const double sigma_delta = Sigma * Delta;
-    const double sigma_delta_sq = sigma_delta * sigma_delta;
-    const double dg_tt_inv_dr = (-(dA_dr * sigma_delta - A * (dSigma_dr * Delta + Sigma * dDelta_dr))
-                                 / sigma_delta_sq);
-    const double dg_tphi_inv_dr = (-(2.0 * M * a * (sigma_delta - r * (dSigma_dr * Delta + Sigma * dDelta_dr)))
-                                   / sigma_delta_sq);
-    const double dg_rr_inv_dr = (dDelta_dr * Sigma - Delta * dSigma_dr) / (Sigma * Sigma);
-    const double dg_thth_inv_dr = -dSigma_dr / (Sigma * Sigma);
-    const double den_phi_dr = Sigma * Delta * sin_th_sq;
-    const double dg_phiphi_inv_dr = ((dDelta_dr * den_phi_dr
-                                      - (Delta - a * a * sin_th_sq)
-                                      * (dSigma_dr * Delta + Sigma * dDelta_dr) * sin_th_sq)
-                                     / (den_phi_dr * den_phi_dr));
+    const double dg_tt_inv_dr = div_by(-(dA_dr * sigma_delta - A * (dSigma_dr * Delta + Sigma * dDelta_dr)),
+                                       sigma_delta_sq, y_SD2);
+    const double dg_tphi_inv_dr = div_by(-(2.0 * M * a * (sigma_delta - r * (dSigma_dr * Delta + Sigma * dDelta_dr))),
+                                         sigma_delta_sq, y_SD2);
+    const double dg_rr_inv_dr = div_by(dDelta_dr * Sigma - Delta * dSigma_dr, sigma_sq, y_S2);
+    const double dg_thth_inv_dr = div_by(-dSigma_dr, sigma_sq, y_S2);
+    const double dg_phiphi_inv_dr = div_by(dDelta_dr * den
+                                           - (Delta - a * a * sin_th_sq)
+                                           * (dSigma_dr * Delta + Sigma * dDelta_dr) * sin_th_sq,
+                                           den_sq, y_den2);
     const double dp_r = -0.5 * (dg_tt_inv_dr * p_t * p_t
                                 + 2.0 * dg_tphi_inv_dr * p_t * p_phi
                                 + dg_rr_inv_dr * p_r * p_r
@@ -101,21 +120,20 @@ __device__ __noinline__ void kerr_rhs(const double (&s)[5], double p_t, double p
                                 + dg_phiphi_inv_dr * p_phi * p_phi);
     const double dSigma_dth = -2.0 * a * a * sin_th * cos_th;
     const double dA_dth = -a * a * Delta * 2.0 * sin_th * cos_th;
-    const double dg_tt_inv_dth = (-(dA_dth * Sigma * Delta - A * dSigma_dth * Delta) / sigma_delta_sq);
-    const double dg_tphi_inv_dth = 2.0 * M * a * r * dSigma_dth / (Sigma * Sigma * Delta);
-    const double dg_rr_inv_dth = -Delta * dSigma_dth / (Sigma * Sigma);
-    const double dg_thth_inv_dth = -dSigma_dth / (Sigma * Sigma);
+    const double dg_tt_inv_dth = div_by(-(dA_dth * Sigma * Delta - A * dSigma_dth * Delta), sigma_delta_sq, y_SD2);
+    const double dg_tphi_inv_dth = div_by(2.0 * M * a * r * dSigma_dth, sigma_sq_delta, y_S2D);
+    const double dg_rr_inv_dth = div_by(-Delta * dSigma_dth, sigma_sq, y_S2);
+    const double dg_thth_inv_dth = div_by(-dSigma_dth, sigma_sq, y_S2);
     const double num = Delta - a * a * sin_th_sq;
-    const double den = Sigma * Delta * sin_th_sq;
     const double dnum_dth = -a * a * 2.0 * sin_th * cos_th;
     const double dden_dth = dSigma_dth * Delta * sin_th_sq + Sigma * Delta * 2.0 * sin_th * cos_th;
-    const double dg_phiphi_inv_dth = (dnum_dth * den - num * dden_dth) / (den * den);
+    const double dg_phiphi_inv_dth = div_by(dnum_dth * den - num * dden_dth, den_sq, y_den2);
     const double dp_th = -0.5 * (dg_tt_inv_dth * p_t * p_t
                                  + 2.0 * dg_tphi_inv_dth * p_t * p_phi
                                  + dg_rr_inv_dth * p_r * p_r
                                  + dg_thth_inv_dth * p_th * p_th
                                  + dg_phiphi_inv_dth * p_phi * p_phi);
-    out[0] = dr; out[1] = dth; out[2] = dphi; out[3] = dp_r; out[4] = dp_th;
+    out.v0 = dr; out.v1 = dth; out.v2 = dphi; out.v3 = dp_r; out.v4 = dp_th;
     } else {
     const double Sigma = r * r + a * a * cos_th * cos_th;
     const double Delta = r * r - 2.0 * M * r + a * a;
@@ -162,8 +180,17 @@ __device__ __noinline__ void kerr_rhs(const double (&s)[5], double p_t, double p
     const double dg_phiphi_inv_dth = (dnum_dth * den - num * dden_dth) * iden2;
     const double dp_th = -0.5 * (dg_tt_inv_dth * pt2 + 2.0 * dg_tphi_inv_dth * ptpp + dg_rr_inv_dth * pr2
                                  + dg_thth_inv_dth * pth2 + dg_phiphi_inv_dth * pp2);
-    out[0] = dr; out[1] = dth; out[2] = dphi; out[3] = dp_r; out[4] = dp_th;
+    out.v0 = dr; out.v1 = dth; out.v2 = dphi; out.v3 = dp_r; out.v4 = dp_th;
     }
+    return out;
+}
+
+template <bool EXACT>
+__device__ __forceinline__ void kerr_rhs(const double (&s)[5], double p_t, double p_phi, double M, double a,
+                                         double r_floor, double (&out)[5])
+{
+    const K5 k = kerr_rhs_regs<EXACT>(s[0], s[1], s[3], s[4], p_t, p_phi, M, a, r_floor);
+    out[0] = k.v0; out[1] = k.v1; out[2] = k.v2; out[3] = k.v3; out[4] = k.v4;
 }
 
 // One Dormand-Prince attempt from (state, k1 = f(state)) with step h: stages 2-7 and the 5th-order
@@ -304,6 +331,7 @@ lp_kerr_kernel(const KerrArgs a, const CamConsts cam)
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
     bool active = false;
+    int pending = 0, pend_event = 2;   // a finished ray waiting for its flush: `done` code, event status
     long long idx = -1;
     double state[5], k1[5];
 #pragma unroll
@@ -317,7 +345,27 @@ lp_kerr_kernel(const KerrArgs a, const CamConsts cam)
     while (true) {
         // ---------------- lane refill ----------------
         const unsigned idle = __ballot_sync(full, !active);
-        if (idle && !queue_empty && (__popc(idle) >= KERR_REFILL_MIN || idle == full)) {
+        const bool flush = idle && (__popc(idle) >= a.refill_min || idle == full);
+        // ---------------- finished rays: final direction + stores, for all waiting lanes at once ----------------
+        if (flush && pending) {
+            double fa = qnan;
+            long long nh = 0;
+            int status = 0;
+            if (pending == 1) status = kerr_extract_angle(state, p_t, p_phi, M, sp, r_capture, pend_event, fa, nh);
+            const double fa_out = (status == 1) ? fa : qnan;                 // metrics.py:678
+            if (a.wide) {
+                ((double *)a.out_fa)[idx] = fa_out;
+                ((long long *)a.out_w)[idx] = nh;
+            } else {
+                ((float *)a.out_fa)[idx] = (float)fa_out;                    // image_lens.py:261
+                const long long c = nh < 0 ? 0 : (nh > 65535 ? 65535 : nh);  // image_lens.py:262
+                ((unsigned short *)a.out_w)[idx] = (unsigned short)c;
+            }
+            if (a.out_status) a.out_status[idx] = (int8_t)status;
+            if (a.out_steps) { a.out_steps[2 * idx] = accepted; a.out_steps[2 * idx + 1] = attempts; }
+            pending = 0;
+        }
+        if (flush && !queue_empty) {
             const int rank = __popc(idle & ((1u << lane) - 1u));
             const long long v = cursor + rank;
             const long long ray = ((v >> 5) * n_warps + warp_id) * 32 + (v & 31);
@@ -390,8 +438,12 @@ lp_kerr_kernel(const KerrArgs a, const CamConsts cam)
                         err_sq += q * q;
                     }
                     const double err_norm = __dsqrt_rn(err_sq / 5.0);
+                    // 0.9 * err_norm ** -0.2 feeds both the reject (metrics.py:517) and the accept
+                    // (metrics.py:562) controller: one pow for the whole warp instead of one per
+                    // divergent branch
+                    const double pow_term = 0.9 * pow(err_norm, -0.2);
                     if (err_norm > 1.0) {                                    // reject, metrics.py:516-522
-                        const double factor = fmax(0.2, 0.9 * pow(err_norm, -0.2));
+                        const double factor = fmax(0.2, pow_term);
                         h *= factor;
                         if (h < h_min) done = 2;
                     } else {
@@ -418,7 +470,7 @@ lp_kerr_kernel(const KerrArgs a, const CamConsts cam)
                             } else if (err_norm < 1e-10) {
                                 h *= 5.0;
                             } else {
-                                h *= fmin(5.0, 0.9 * pow(err_norm, -0.2));
+                                h *= fmin(5.0, pow_term);
                             }
                         }
                     }
@@ -426,22 +478,9 @@ lp_kerr_kernel(const KerrArgs a, const CamConsts cam)
             }
         }
 
-        if (done) {
-            double fa = qnan;
-            long long nh = 0;
-            int status = 0;
-            if (done == 1) status = kerr_extract_angle(state, p_t, p_phi, M, sp, r_capture, event_status, fa, nh);
-            const double fa_out = (status == 1) ? fa : qnan;                 // metrics.py:678
-            if (a.wide) {
-                ((double *)a.out_fa)[idx] = fa_out;
-                ((long long *)a.out_w)[idx] = nh;
-            } else {
-                ((float *)a.out_fa)[idx] = (float)fa_out;                    // image_lens.py:261
-                const long long c = nh < 0 ? 0 : (nh > 65535 ? 65535 : nh);  // image_lens.py:262
-                ((unsigned short *)a.out_w)[idx] = (unsigned short)c;
-            }
-            if (a.out_status) a.out_status[idx] = (int8_t)status;
-            if (a.out_steps) { a.out_steps[2 * idx] = accepted; a.out_steps[2 * idx + 1] = attempts; }
+        if (done) {          // park the lane: its result is produced in the next flush phase
+            pending = done;
+            pend_event = event_status;
             active = false;
         }
     }
@@ -469,6 +508,13 @@ static int kerr_launch(KerrArgs &a, const CamConsts &cam, cudaStream_t stream)
     a.sin_th_obs = sin(a.theta_obs);
     a.cos_th_obs = cos(a.theta_obs);
     const bool fast = kerr_fast_rhs();
+    static int refill = 0;
+    if (!refill) {
+        const char *e = getenv("LP_KERR_REFILL");
+        const int v = e ? atoi(e) : 0;
+        refill = (v >= 1 && v <= 32) ? v : KERR_REFILL_MIN;
+    }
+    a.refill_min = refill;
     // resident CTAs per SM ptxas must fit (register cap): the kernel is latency-bound, so more
     // resident warps win until the spills cost more (LP_KERR_MINB = 2..6, tuning knob)
     static int minb = 0;

@@ -48,6 +48,28 @@ def test_alpha_lookup_golden(native, golden, tag):
     assert d.max() <= 1 and (d > 0).mean() < 1e-3
 
 
+@pytest.mark.parametrize("decimals", [0, 2, 3, 6])
+def test_alpha_lookup_decimals(native, oracle, decimals):
+    """build_alpha_lookup(decimals=d) bins alpha with np.round before the float32 cast
+    (image_lens.py:150-151): rint(alpha * 10^d) / 10^d on the device.  A 1-ulp arccos difference
+    can move a value across a bin edge only where alpha * 10^d sits on a half-integer."""
+    il = _il()
+    H, W = 360, 640
+    vfov = np.radians(40.0)
+    fov = (2 * np.arctan(np.tan(vfov / 2) * W / H), vfov)
+    for psi in [(0.0, 0.0), (0.21, -0.13)]:
+        ref = oracle.build_alpha_lookup((H, W), fov, decimals=decimals, psi=psi)
+        a = il.build_alpha_lookup((H, W), fov, decimals=decimals, psi=psi)
+        assert a.dtype == np.float32 and a.shape == ref.shape
+        d = _f32_ulp_diff(a, ref)
+        moved = d > 1
+        assert moved.sum() <= 2, "%d values landed in another bin" % int(moved.sum())
+        assert np.all(np.abs(a[moved].astype(np.float64) - ref[moved]) <= 1.0001 * 10.0 ** -decimals)
+        assert (d > 0).mean() < 1e-3
+        # the binned table really is binned: at most ~pi * 10^d + 1 distinct values
+        assert np.unique(a).size <= int(np.pi * 10 ** decimals) + 2
+
+
 @pytest.mark.parametrize("tag", TAGS)
 def test_trace_alpha_table_golden(native, golden, tag):
     """Reference alpha table in -> final_alpha float32 / winding uint16 out (image_lens.py:155-178)."""
