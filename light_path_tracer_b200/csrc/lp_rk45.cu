@@ -34,8 +34,8 @@
 #include <stdlib.h>
 
 #define RK_BLOCK 128
-#define RK_REFILL_MIN 4
-#define RK_DEFAULT_MINB 2
+#define RK_REFILL_MIN 8
+#define RK_DEFAULT_MINB 3
 #define RK_NC 6            /* moving components: t, r, theta, phi, p_r, p_theta */
 
 static __constant__ double c_A[6][5] = {
@@ -73,6 +73,7 @@ struct Rk45Args {
     double *traj;               // optional [n][max_points][9]
     int32_t max_points;
     int32_t *n_points;          // optional [n]
+    int32_t refill_min;         // lanes that must be waiting before a flush (RK_REFILL_MIN)
 };
 
 struct ThetaCache { double th, s, c; };
@@ -285,7 +286,7 @@ lp_rk45_kernel(const Rk45Args a)
     while (true) {
         // ---------------- lane refill (ballot + rank) ----------------
         const unsigned idle = __ballot_sync(full, !active);
-        if (idle && !queue_empty && (__popc(idle) >= RK_REFILL_MIN || idle == full)) {
+        if (idle && !queue_empty && (__popc(idle) >= a.refill_min || idle == full)) {
             const int rank = __popc(idle & ((1u << lane) - 1u));
             const long long v = cursor + rank;               // meaningful on idle lanes only
             const long long ray = ((v >> 5) * n_warps + warp_id) * 32 + (v & 31);
@@ -436,8 +437,11 @@ lp_rk45_kernel(const Rk45Args a)
                 esum = fma(e, e, esum);
             }
             const double error_norm = rms8(esum);
+            // one pow for the accept and the reject controller (rk.py:155-170): divergent branches
+            // would each run their own copy for the whole warp
+            const double pow_term = 0.9 * pow(error_norm, -0.2);
             if (error_norm < 1) {
-                double factor = (error_norm == 0) ? 10.0 : fmin(10.0, 0.9 * pow(error_norm, -0.2));
+                double factor = (error_norm == 0) ? 10.0 : fmin(10.0, pow_term);
                 if (rejected) factor = fmin(1.0, factor);
                 ha *= factor;
                 // ---- accepted: events on the new point (ivp.py:676-699) ----
@@ -488,7 +492,7 @@ lp_rk45_kernel(const Rk45Args a)
                 for (int i = 0; i < RK_NC; ++i) { y[i] = y_new[i]; f[i] = K[6][i]; }
                 fresh = true;
             } else {
-                ha *= fmax(0.2, 0.9 * pow(error_norm, -0.2));
+                ha *= fmax(0.2, pow_term);
                 rejected = true;
             }
         }
@@ -538,13 +542,22 @@ static int rk45_launch(bool metric_is_kerr, double kerr_a, const double *alphas,
     a.out_nsteps = out_nsteps; a.out_status = out_status;
     a.traj = traj; a.max_points = max_points; a.n_points = n_points;
     // resident CTAs per SM ptxas must fit: 2 -> 202 registers, no spills; 3 -> 168; 4 -> 128 (spills).
-    // LP_RK45_MINB selects (tuning knob); the default is the measured best.
+    // LP_RK45_MINB selects (tuning knob); the default is the measured best (4K frame: 2 -> 184 ms,
+    // 3 -> 154 ms, 4 -> 164 ms: the kernel is bound by the latency of the right-hand side's dependent
+    // chains, so resident warps win until the spills start).
     static int minb = 0;
     if (!minb) {
         const char *e = getenv("LP_RK45_MINB");
         const int v = e ? atoi(e) : 0;
         minb = (v == 2 || v == 3 || v == 4) ? v : RK_DEFAULT_MINB;
     }
+    static int refill = 0;
+    if (!refill) {
+        const char *e = getenv("LP_RK45_REFILL");
+        const int v = e ? atoi(e) : 0;
+        refill = (v >= 1 && v <= 32) ? v : RK_REFILL_MIN;
+    }
+    a.refill_min = refill;
     const bool kerr = metric_is_kerr;
     const void *fn = kerr ? (const void *)lp_rk45_kernel<2, 1>
                    : minb == 2 ? (const void *)lp_rk45_kernel<2, 0>

@@ -8,7 +8,7 @@ m = Schwarzschild(1.0)
 for (H, W) in [(270, 480), (1080, 1920), (2160, 3840)][: int(sys.argv[1]) if len(sys.argv) > 1 else 3]:
     vfov = np.radians(40.0); fov = (2*np.arctan(np.tan(vfov/2)*W/H), vfov)
     a = il.build_alpha_lookup((H, W), fov, device=True).double()
-    for rep in range(2):
+    for rep in range(3):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         state, lam, oc, ns = gt.trace_rays(m, 100.0, a)
