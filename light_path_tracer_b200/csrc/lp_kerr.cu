@@ -6,16 +6,16 @@
 // per-pixel driver precompute_final_alpha_lookup_2d (image_lens.py:185-280).
 //
 // GPU layout: persistent warps, one ray per LANE, every trip of the main loop is one step
-// ATTEMPT (accepted or rejected) for all 32 lanes.  A lane whose ray has ended PARKS with its
-// final state; once >= KERR_REFILL_MIN lanes are parked or empty (ballot) the warp runs one
-// flush phase: final direction + stores for all parked lanes together, then the next rays of
-// the warp's queue are initialised into the free lanes together (ballot + rank).  The divergent
-// per-ray work (extract angle: ~600 instructions, initial conditions + first right-hand side:
-// ~1500) is thereby paid once per ~8 rays instead of once per ray, and captured / escaped rays
-// stop occupying lanes (adaptive step counts differ 3x between neighbouring rays near the
-// shadow edge).  State, the seven stage vectors and the controller live in registers, fp64;
-// the right-hand side is one __noinline__ function (arguments and results in registers) so the
-// hot loop stays inside the instruction cache.  No shared memory, no atomics, no hidden state.
+// ATTEMPT (accepted or rejected) for all 32 lanes; a lane whose ray has ended takes another ray
+// of its warp's queue, so captured / escaped rays stop occupying lanes (adaptive step counts
+// differ 3x between neighbouring rays near the shadow edge).  The divergent per-ray work
+// (initial conditions + first right-hand side: ~1500 instructions; final direction: ~600) is
+// never run for a single lane: lp_kerr_queued_kernel (the default, see there) prepares and
+// retires rays 32 at a time through per-warp queues in shared memory; lp_kerr_kernel
+// (LP_KERR_QUEUE=0) parks finished lanes and serves them in one flush phase once
+// KERR_REFILL_MIN lanes wait.  State, the seven stage vectors and the controller live in
+// registers, fp64; the right-hand side is one __noinline__ function (arguments and results in
+// registers) so the hot loop stays inside the instruction cache.  No atomics, no hidden state.
 //
 // Arithmetic: every expression is written in the reference's order and the library is built
 // with -fmad=false, so all +,-,*,/ and sqrt round exactly like the numba build; what differs
@@ -486,6 +486,263 @@ lp_kerr_kernel(const KerrArgs a, const CamConsts cam)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Queued variant (the default): the two divergent per-ray phases run CONVERGED on whole batches.
+//   * in-queue: when a warp runs out of prepared rays, all 32 lanes together compute the initial
+//     conditions and the first right-hand side of the next 32 rays of its queue into shared
+//     memory (coalesced alpha reads); empty lanes pop prepared rays one by one, in every trip,
+//     so a finished lane is stepping again in the next trip (no refill threshold, no waiting);
+//   * out-queue: a finished lane pushes its final state to shared memory and is free at once;
+//     when 32 results have gathered, all 32 lanes extract the final directions together.
+// Same rays, same operations per ray, bit-identical outputs; only the lane a ray runs in differs.
+// Shared memory: 5.1 KB per warp.
+#define KQ_IN 10      /* r, theta, p_r, p_theta, p_phi, k1[0..4] */
+#define KQ_OUT 6      /* r, theta, phi, p_r, p_theta, p_phi */
+
+struct KerrWarpQueues {
+    double in[KQ_IN][32];
+    double out[KQ_OUT][32];
+    long long out_idx[32];
+    int out_accepted[32], out_attempts[32], out_code[32];   // code = done | (event_status + 1) << 2
+    int in_flag[32];                                        // bit 0 valid, bit 1 axis_refine
+};
+
+__device__ __forceinline__ void kerr_store_result(const KerrArgs &a, long long idx, int status, double fa,
+                                                  long long nh, int accepted, int attempts)
+{
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    const double fa_out = (status == 1) ? fa : qnan;                         // metrics.py:678
+    if (a.wide) {
+        ((double *)a.out_fa)[idx] = fa_out;
+        ((long long *)a.out_w)[idx] = nh;
+    } else {
+        ((float *)a.out_fa)[idx] = (float)fa_out;                            // image_lens.py:261
+        const long long c = nh < 0 ? 0 : (nh > 65535 ? 65535 : nh);          // image_lens.py:262
+        ((unsigned short *)a.out_w)[idx] = (unsigned short)c;
+    }
+    if (a.out_status) a.out_status[idx] = (int8_t)status;
+    if (a.out_steps) { a.out_steps[2 * idx] = accepted; a.out_steps[2 * idx + 1] = attempts; }
+}
+
+template <bool EXACT, int MINB>
+__global__ void __launch_bounds__(KERR_BLOCK, MINB)
+lp_kerr_queued_kernel(const KerrArgs a, const CamConsts cam)
+{
+    __shared__ KerrWarpQueues queues[KERR_BLOCK / 32];
+    KerrWarpQueues &Q = queues[threadIdx.x >> 5];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const double M = a.M, sp = a.a, r_floor = a.r_plus * 1.001;
+    const double r_capture = a.r_plus * 1.01, r_escape = a.r_obs * 2.0, lambda_max = a.lambda_max;
+    const double h_min = 1e-12;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    const double p_t = -1.0;                    // -E with E = 1 (metrics.py:196, :203)
+
+    bool active = false;
+    int pending = 0, pend_event = 2;
+    long long idx = -1;
+    double state[5], k1[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) { state[i] = 0.0; k1[i] = 0.0; }
+    double p_phi = 0.0, lam = 0.0, h = 1.0, atol = 1e-8, rtol = 1e-6;
+    int accepted = 0, attempts = 0, iters = 0;
+
+    // warp-uniform queue state.  Chunk c of this warp = rays (c * n_warps + warp_id) * 32 + 0..31
+    long long chunk = 0, in_ray0 = 0;
+    int in_base = 0, in_avail = 0, out_count = 0;
+    bool queue_empty = (warp_id * 32 >= a.n);
+
+    while (true) {
+        // ---------------- finished lanes -> out-queue ----------------
+        const unsigned fin = __ballot_sync(full, pending != 0);
+        const bool last_round = !fin && queue_empty && in_avail == 0 && !__any_sync(full, active);
+        if (out_count && (out_count + __popc(fin) > 32 || last_round)) {
+            // all lanes together: final direction + stores for the gathered results
+            __syncwarp();
+            if (lane < out_count) {
+                double st[5];
+#pragma unroll
+                for (int i = 0; i < 5; ++i) st[i] = Q.out[i][lane];
+                const double o_p_phi = Q.out[5][lane];
+                const int code = Q.out_code[lane];
+                double fa = qnan;
+                long long nh = 0;
+                int status = 0;
+                if ((code & 3) == 1)
+                    status = kerr_extract_angle(st, p_t, o_p_phi, M, sp, r_capture, (code >> 2) - 1, fa, nh);
+                kerr_store_result(a, Q.out_idx[lane], status, fa, nh, Q.out_accepted[lane], Q.out_attempts[lane]);
+            }
+            __syncwarp();
+            out_count = 0;
+        }
+        if (fin) {
+            if (pending) {
+                const int slot = out_count + __popc(fin & lt_mask);
+#pragma unroll
+                for (int i = 0; i < 5; ++i) Q.out[i][slot] = state[i];
+                Q.out[5][slot] = p_phi;
+                Q.out_idx[slot] = idx;
+                Q.out_accepted[slot] = accepted;
+                Q.out_attempts[slot] = attempts;
+                Q.out_code[slot] = pending | ((pend_event + 1) << 2);
+                pending = 0;
+            }
+            out_count += __popc(fin);
+        }
+        if (last_round) {
+            if (out_count) continue;            // (cannot happen: !fin on the last round)
+            break;
+        }
+
+        // ---------------- empty lanes <- in-queue ----------------
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            const unsigned empty = __ballot_sync(full, !active);
+            if (!empty) break;
+            if (in_avail == 0) {
+                if (queue_empty) break;
+                // all lanes together: initial conditions + FSAL seed of the next 32 rays
+                in_ray0 = (chunk * n_warps + warp_id) * 32;
+                const long long ray = in_ray0 + lane;
+                int flag = 0;
+                __syncwarp();
+                if (ray < a.n) {
+                    double alpha, theta;
+                    bool refine;
+                    if (a.frame_mode) {
+                        int row, col;
+                        pixel_row_col(ray, a.n, cam.width, a.row0, row, col);
+                        alpha = (double)__ldg(a.alpha32 + ray);             // image_lens.py:247
+                        theta = pixel_theta(cam, row, col);
+                        refine = a.refine_cols ? (__ldg(a.refine_cols + col) != 0) : false;
+                    } else {
+                        alpha = __ldg(a.alphas + ray);
+                        theta = __ldg(a.thetas + ray);
+                        refine = a.refine ? (__ldg(a.refine + ray) != 0) : false;
+                    }
+                    double s0[5], kk[5], i_p_t, i_p_phi;
+                    const bool ok = kerr_init(M, sp, a.r_obs, alpha, theta, a.theta_obs, a.sin_th_obs, a.cos_th_obs,
+                                              s0, i_p_t, i_p_phi);
+                    if (ok) {
+                        kerr_rhs<EXACT>(s0, p_t, i_p_phi, M, sp, r_floor, kk);   // FSAL seed, metrics.py:447
+                        Q.in[0][lane] = s0[0]; Q.in[1][lane] = s0[1]; Q.in[2][lane] = s0[3]; Q.in[3][lane] = s0[4];
+                        Q.in[4][lane] = i_p_phi;
+#pragma unroll
+                        for (int i = 0; i < 5; ++i) Q.in[5 + i][lane] = kk[i];
+                    }
+                    flag = (ok ? 1 : 0) | (refine ? 2 : 0);
+                }
+                Q.in_flag[lane] = flag;
+                __syncwarp();
+                const long long left = a.n - in_ray0;
+                in_avail = left < 32 ? (int)left : 32;
+                in_base = 0;
+                chunk++;
+                queue_empty = ((chunk * n_warps + warp_id) * 32 >= a.n);
+            }
+            const int rank = __popc(empty & lt_mask);
+            if (!active && rank < in_avail) {
+                const int e = in_base + rank;
+                const int flag = Q.in_flag[e];
+                idx = in_ray0 + e;
+                if (flag & 1) {
+                    state[0] = Q.in[0][e]; state[1] = Q.in[1][e]; state[2] = 0.0;
+                    state[3] = Q.in[2][e]; state[4] = Q.in[3][e];
+                    p_phi = Q.in[4][e];
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) k1[i] = Q.in[5 + i][e];
+                    atol = (flag & 2) ? 1e-10 : 1e-8;                       // metrics.py:432-433
+                    rtol = (flag & 2) ? 1e-8 : 1e-6;
+                    lam = 0.0;
+                    h = fmax(1.0, 0.01 * a.r_obs);
+                    accepted = 0; attempts = 0; iters = 0;
+                    active = true;
+                } else {
+                    kerr_store_result(a, idx, 0, qnan, 0, 0, 0);            // initial conditions invalid: status 0
+                }
+            }
+            const int taken = min(__popc(empty), in_avail);
+            in_base += taken;
+            in_avail -= taken;
+        }
+        if (!active) continue;
+
+        // ---------------- one trip of the reference's `for _step in range(max_steps)` ----------------
+        int done = 0;            // 0 running, 1 finished -> extract angle, 2 invalid (status 0)
+        int event_status = 2;
+        if (iters >= 200000 || lam >= lambda_max) {
+            done = 1;
+        } else {
+            iters++;
+            const double remaining = lambda_max - lam;
+            if (h > remaining) h = remaining;
+            if (h <= 0.0) {
+                done = 1;
+            } else {
+                attempts++;
+                double k3[5], k4[5], k5[5], k6[5], k7[5], nxt[5];
+                kerr_dp_stages<EXACT>(state, k1, h, p_t, p_phi, M, sp, r_floor, k3, k4, k5, k6, k7, nxt);
+
+                if (!finite5(nxt) || nxt[0] <= 0.0) {                        // metrics.py:498-503
+                    h *= 0.25;
+                    if (h < h_min) done = 2;
+                } else {
+                    double err_sq = 0.0;
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) {
+                        const double ei = h * (kE1 * k1[i] + kE3 * k3[i] + kE4 * k4[i] + kE5 * k5[i] + kE6 * k6[i]
+                                               + kE7 * k7[i]);
+                        const double sc = atol + rtol * fmax(fabs(state[i]), fabs(nxt[i]));
+                        const double q = ei / sc;
+                        err_sq += q * q;
+                    }
+                    const double err_norm = __dsqrt_rn(err_sq / 5.0);
+                    const double pow_term = 0.9 * pow(err_norm, -0.2);       // metrics.py:517, :562
+                    if (err_norm > 1.0) {                                    // reject, metrics.py:516-522
+                        h *= fmax(0.2, pow_term);
+                        if (h < h_min) done = 2;
+                    } else {
+                        accepted++;
+                        const double r_prev = state[0], r_next = nxt[0];
+                        const bool cap = (r_prev > r_capture && r_next <= r_capture);
+                        const bool esc = !cap && (r_prev < r_escape && r_next >= r_escape);
+                        if (cap || esc) {                                    // metrics.py:528-550
+                            const double target = cap ? r_capture : r_escape;
+                            const double denom = r_next - r_prev;
+                            double frac = (denom == 0.0) ? 1.0 : (target - r_prev) / denom;
+                            frac = clip_scalar(frac, 0.0, 1.0);
+#pragma unroll
+                            for (int i = 0; i < 5; ++i) state[i] = state[i] + frac * (nxt[i] - state[i]);
+                            lam += frac * h;
+                            event_status = cap ? -1 : 1;
+                            done = 1;
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 5; ++i) { state[i] = nxt[i]; k1[i] = k7[i]; }
+                            lam += h;
+                            if (!finite5(state)) {
+                                done = 2;
+                            } else if (err_norm < 1e-10) {
+                                h *= 5.0;
+                            } else {
+                                h *= fmin(5.0, pow_term);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (done) {
+            pending = done;
+            pend_event = event_status;
+            active = false;
+        }
+    }
+}
+
 // LP_KERR_FAST=1 selects the shared-reciprocal right-hand side (2.7x faster).  NOT the default: with
 // the tight axis_refine tolerances (rtol 1e-8) the error norm is a 9-digit cancellation, a few ulp
 // in the stages move the step sizes by ~1e-8, and the reference's LINEAR interpolation at the exit
@@ -532,6 +789,24 @@ static int kerr_launch(KerrArgs &a, const CamConsts &cam, cudaStream_t stream)
         if (chunks < grid) grid = (int)chunks; \
         lp_kerr_kernel<EX, MB><<<grid, KERR_BLOCK, 0, stream>>>(a, cam); \
     } while (0)
+    const char *qe = getenv("LP_KERR_QUEUE");
+    const bool queued = !(qe && atoi(qe) == 0);
+#define KERR_DISPATCH_Q(EX, MB) \
+    do { \
+        int grid = 0; \
+        int rc = lp_grid_for((const void *)lp_kerr_queued_kernel<EX, MB>, KERR_BLOCK, &grid); \
+        if (rc != LP_OK) return rc; \
+        const long long chunks = (a.n + KERR_BLOCK - 1) / KERR_BLOCK; \
+        if (chunks < grid) grid = (int)chunks; \
+        lp_kerr_queued_kernel<EX, MB><<<grid, KERR_BLOCK, 0, stream>>>(a, cam); \
+    } while (0)
+    if (queued && !fast) {
+        if (minb == 3) { KERR_DISPATCH_Q(true, 3); }
+        else if (minb == 5) { KERR_DISPATCH_Q(true, 5); }
+        else { KERR_DISPATCH_Q(true, 4); }
+        return lp_check_launch();
+    }
+#undef KERR_DISPATCH_Q
     if (fast) { KERR_DISPATCH(false, 2); }
     else if (minb == 2) { KERR_DISPATCH(true, 2); }
     else if (minb == 3) { KERR_DISPATCH(true, 3); }

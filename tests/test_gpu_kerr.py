@@ -225,3 +225,34 @@ def test_kerr_views_tensor_lookup_and_odd_inputs(native, oracle):
     assert (nt, ntr) == (nt2, ntr2) == (H * W, H * W // 2)
     assert bits_equal(fa_n, fa_t.cpu().numpy()) and np.array_equal(w_n, w_t.cpu().numpy())
     assert bits_equal(fa_n[H - H // 2:], fa_n[:H // 2][::-1])                     # top/bottom mirror
+
+
+def test_kerr_queued_equals_parked_kernel(native, monkeypatch):
+    """The two schedules of the Kerr kernel (in/out queues in shared memory = the default;
+    LP_KERR_QUEUE=0 = lanes parked until a batched flush) run the same operations per ray:
+    every output bit must agree, on a frame tile and on a ragged batch with refine flags."""
+    import torch
+    from light_path_tracer_b200 import image_lens as il, _device as dev
+    m = _kerr(1.0, 0.9)
+    H, W = 135, 243
+    vfov = np.radians(40.0)
+    fov = (2 * np.arctan(np.tan(vfov / 2) * W / H), vfov)
+    a32 = il.build_alpha_lookup((H, W), fov, device=True)
+    cam = dev.camera_vector((H, W), fov, (0.0, 0.0), il._psi_frame)
+    rng = np.random.default_rng(11)
+    n = 32 * 37 + 5
+    alpha = np.concatenate([rng.uniform(0.0, 0.3, n - 3), [0.0, np.pi, 1e-9]])
+    theta = rng.uniform(-np.pi, np.pi, n)
+    refine = rng.random(n) < 0.2
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("LP_KERR_QUEUE", mode)
+        steps = torch.empty((H, W, 2), dtype=torch.int32, device="cuda")
+        fa, w = m.trace_alpha_table_2d(a32, cam, 100.0, 1.1, steps=steps)
+        out_fa = np.empty(n)
+        out_w = np.empty(n, dtype=np.int64)
+        m.trace_rays_batch(100.0, alpha, theta, 1.1, refine, out_fa, out_w)
+        res[mode] = (fa.cpu().numpy(), w.cpu().numpy(), steps.cpu().numpy(), out_fa, out_w)
+    for x, y in zip(res["1"], res["0"]):
+        assert bits_equal(x, y)
+    assert np.isfinite(res["1"][0]).sum() > 0.9 * H * W
