@@ -268,21 +268,21 @@ def run_gpu(args):
 
     # end to end through the host-buffer API (image_lens.HostFramePipeline): per frame, the
     # source image goes pinned host -> device, the fused kernel renders this rank's tile, the
-    # tile goes device -> pinned host; two streams, so one frame's H2D overlaps the previous
-    # frame's D2H.  Timed as K frames between two events on the current stream.
+    # tile goes device -> pinned host; three slots on three streams, so one frame's H2D overlaps the
+    # previous frame's D2H and the render in between leaves no bubble on either copy engine.  Timed as K frames between two events on the current stream.
     # N > 1 (dist.ShardedHostFrames): every rank uploads only ITS rows of the source over its own
     # PCIe link and an NCCL all-gather over NVLink replicates the source on every GPU.
-    tile_hosts = [tile_host, torch.empty((rows, W, 3), dtype=torch.float32).pin_memory()]
+    tile_hosts = [tile_host] + [torch.empty((rows, W, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
     if N == 1:
-        host_pipe = il.HostFramePipeline((H, W, 3), torch.float32, VFOV_DEG, metric, depth=2)
+        host_pipe = il.HostFramePipeline((H, W, 3), torch.float32, VFOV_DEG, metric, depth=3)
 
         def submit(j):
-            host_pipe.submit(src_host, R_OBS, out=tile_hosts[j % 2], rows=(row0, rows), fov=fov)
+            host_pipe.submit(src_host, R_OBS, out=tile_hosts[j % 3], rows=(row0, rows), fov=fov)
     else:
-        host_pipe = lpdist.ShardedHostFrames((H, W, 3), torch.float32, metric=metric, depth=2)
+        host_pipe = lpdist.ShardedHostFrames((H, W, 3), torch.float32, metric=metric, depth=3)
 
         def submit(j):
-            host_pipe.submit(src_host, fov, R_OBS, out=tile_hosts[j % 2])
+            host_pipe.submit(src_host, fov, R_OBS, out=tile_hosts[j % 3])
 
     def run_e2e(k):
         for j in range(k):
@@ -332,7 +332,7 @@ def run_gpu(args):
     total_e2e = float(timed_e2e(args.steps))
     # the frame that came back through the host path is the frame the resident path renders
     il.render_frame(src, fov, R_OBS, metric, rows=(row0, rows), out=local_tile)
-    if not torch.equal(tile_hosts[(args.steps - 1) % 2], local_tile.cpu()):
+    if not torch.equal(tile_hosts[(args.steps - 1) % 3], local_tile.cpu()):
         raise SystemExit("e2e frame differs from the device-resident frame")
 
     # dominant kernel alone (no gather), same events: roofline numerator / denominator
@@ -451,11 +451,11 @@ def run_gpu(args):
                     "h2d_bytes_per_step": int(src_host.numel() * 4),
                     "d2h_bytes_per_step": int(rays * 12),
                     "path": ("image_lens.HostFramePipeline: pinned float32 source -> H2D -> lp_render_frame -> D2H "
-                             "pinned float32 frame, every frame; 2 streams (frame k+1's H2D overlaps frame k's D2H)")
+                             "pinned float32 frame, every frame; 3 slots on 3 streams (frame k+1's H2D overlaps frame k's D2H; the third slot covers the render between them)")
                     if N == 1 else
                             ("dist.ShardedHostFrames: every rank uploads its 1/N of the pinned float32 source, NCCL "
                              "all-gather replicates it over NVLink, lp_render_frame renders the rank's tile, D2H of "
-                             "the tile to pinned memory, every frame; 2 streams")},
+                             "the tile to pinned memory, every frame; 3 slots on 3 streams")},
             "gpu_launches": args.steps * (len(bg.bands) if bg is not None else 1),
             "gather": gather_mode,
             "roofline": {"bound": "fp64", "kernel": "lp_render_kernel (alpha + Binet RK4 + remap, fused)",

@@ -170,7 +170,7 @@ class ShardedHostFrames:
     all of it; two slots on two streams overlap one frame's upload with the previous frame's
     download, as image_lens.HostFramePipeline does on one GPU.  Needs equal row tiles."""
 
-    def __init__(self, shape, dtype, vertical_fov=None, metric=None, depth=2, group=None):
+    def __init__(self, shape, dtype, vertical_fov=None, metric=None, depth=3, group=None):
         import torch
         import torch.distributed as dist
         from .metrics import Schwarzschild

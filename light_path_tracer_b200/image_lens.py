@@ -428,7 +428,9 @@ class HostFramePipeline:
     changing background): every frame's source is copied from (pinned) host memory, rendered
     by the fused kernel and copied back, on ``depth`` CUDA streams with their own device
     buffers, so frame k+1's host->device copy overlaps frame k's device->host copy (PCIe is
-    full duplex) and the render hides under both.
+    full duplex) and the render hides under both.  depth = 3: a slot is busy for upload + render
+    + download (2.1 + 0.9 + 2.1 ms at 4K float32), so two slots leave a bubble on the copy
+    engines (2.5 ms per frame); three reach the duplex PCIe rate (2.1 ms, tools/pcie_probe.py).
 
         pipe = HostFramePipeline((H, W, 3), torch.float32, 40.0, metric)
         for src, dst in zip(host_sources, host_frames):     # pinned CPU tensors
@@ -438,7 +440,7 @@ class HostFramePipeline:
     ``rows=(row0, n)`` renders a row tile of the frame (multi-GPU sharding); ``out`` then
     has n rows."""
 
-    def __init__(self, shape, dtype, vertical_fov_deg=40.0, metric=None, depth=2, unit_u8=False):
+    def __init__(self, shape, dtype, vertical_fov_deg=40.0, metric=None, depth=3, unit_u8=False):
         t = dev.torch()
         self.unit_u8 = bool(unit_u8)      # uint8 frames standing for float32/255 (see render_lensed_image)
         self.metric = metric if metric is not None else Schwarzschild(M=1.0)
