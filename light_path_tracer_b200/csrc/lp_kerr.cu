@@ -225,6 +225,39 @@ __device__ __forceinline__ void kerr_dp_stages(const double (&state)[5], const d
     kerr_rhs<EXACT>(nxt, p_t, p_phi, M, sp, r_floor, k7);
 }
 
+// Sum of squared scaled errors (metrics.py:505-513).  The five quotients e_i / scale_i are formed
+// with the branch-free division halves (bit-identical to `/` for finite operands, scale >= atol
+// > 0; a numerator below 2^-960 squares to zero either way), so the five dependent chains
+// interleave instead of each waiting behind its own slow-path branch; anything non-finite
+// takes the literal IEEE form.
+__device__ __forceinline__ double kerr_err_sq(const double (&state)[5], const double (&nxt)[5],
+                                              const double (&k1)[5], const double (&k3)[5], const double (&k4)[5],
+                                              const double (&k5)[5], const double (&k6)[5], const double (&k7)[5],
+                                              double h, double atol, double rtol)
+{
+    double e[5], sc[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        e[i] = h * (kE1 * k1[i] + kE3 * k3[i] + kE4 * k4[i] + kE5 * k5[i] + kE6 * k6[i] + kE7 * k7[i]);
+        sc[i] = atol + rtol * fmax(fabs(state[i]), fabs(nxt[i]));
+    }
+    double err_sq = 0.0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const double q = div_by(e[i], sc[i], div_rcp(sc[i]));
+        err_sq += q * q;
+    }
+    if (!isfinite(err_sq)) {
+        err_sq = 0.0;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const double q = e[i] / sc[i];
+            err_sq += q * q;
+        }
+    }
+    return err_sq;
+}
+
 // metrics.py:148-224.  false = (ok == False) -> status 0.
 __device__ __forceinline__ bool kerr_init(double M, double a, double r_obs, double alpha, double theta,
                                           double theta_obs, double sin_th, double cos_th,
@@ -428,15 +461,7 @@ lp_kerr_kernel(const KerrArgs a, const CamConsts cam)
                     h *= 0.25;
                     if (h < h_min) done = 2;
                 } else {
-                    double err_sq = 0.0;
-#pragma unroll
-                    for (int i = 0; i < 5; ++i) {
-                        const double ei = h * (kE1 * k1[i] + kE3 * k3[i] + kE4 * k4[i] + kE5 * k5[i] + kE6 * k6[i]
-                                               + kE7 * k7[i]);
-                        const double sc = atol + rtol * fmax(fabs(state[i]), fabs(nxt[i]));
-                        const double q = ei / sc;
-                        err_sq += q * q;
-                    }
+                    const double err_sq = kerr_err_sq(state, nxt, k1, k3, k4, k5, k6, k7, h, atol, rtol);
                     const double err_norm = __dsqrt_rn(err_sq / 5.0);
                     // 0.9 * err_norm ** -0.2 feeds both the reject (metrics.py:517) and the accept
                     // (metrics.py:562) controller: one pow for the whole warp instead of one per
@@ -690,15 +715,7 @@ lp_kerr_queued_kernel(const KerrArgs a, const CamConsts cam)
                     h *= 0.25;
                     if (h < h_min) done = 2;
                 } else {
-                    double err_sq = 0.0;
-#pragma unroll
-                    for (int i = 0; i < 5; ++i) {
-                        const double ei = h * (kE1 * k1[i] + kE3 * k3[i] + kE4 * k4[i] + kE5 * k5[i] + kE6 * k6[i]
-                                               + kE7 * k7[i]);
-                        const double sc = atol + rtol * fmax(fabs(state[i]), fabs(nxt[i]));
-                        const double q = ei / sc;
-                        err_sq += q * q;
-                    }
+                    const double err_sq = kerr_err_sq(state, nxt, k1, k3, k4, k5, k6, k7, h, atol, rtol);
                     const double err_norm = __dsqrt_rn(err_sq / 5.0);
                     const double pow_term = 0.9 * pow(err_norm, -0.2);       // metrics.py:517, :562
                     if (err_norm > 1.0) {                                    // reject, metrics.py:516-522

@@ -423,18 +423,33 @@ lp_rk45_kernel(const Rk45Args a)
             }
             rk_f<METRIC>(a, r_floor, p_t, p_phi, y_new, tc, K[6]);
             // ---- error norm, rk.py:105-109, :148-149 ----
-            double esum = 0.0;
+            // the six quotients use the branch-free division halves (bit-identical to `/` for
+            // finite operands, scale >= atol > 0) so their dependent chains interleave; anything
+            // non-finite takes the literal IEEE form
+            double esum = 0.0, en[RK_NC], es[RK_NC];
 #pragma unroll
             for (int i = 0; i < RK_NC; ++i) {
-                const double scale = atol + fmax(fabs(y[i]), fabs(y_new[i])) * rtol;
+                es[i] = atol + fmax(fabs(y[i]), fabs(y_new[i])) * rtol;
                 double acc = K[0][i] * c_E[0];
                 acc = fma(K[2][i], c_E[2], acc);
                 acc = fma(K[3][i], c_E[3], acc);
                 acc = fma(K[4][i], c_E[4], acc);
                 acc = fma(K[5][i], c_E[5], acc);
                 acc = fma(K[6][i], c_E[6], acc);
-                const double e = acc * h / scale;
+                en[i] = acc * h;
+            }
+#pragma unroll
+            for (int i = 0; i < RK_NC; ++i) {
+                const double e = div_by(en[i], es[i], div_rcp(es[i]));
                 esum = fma(e, e, esum);
+            }
+            if (!isfinite(esum)) {
+                esum = 0.0;
+#pragma unroll
+                for (int i = 0; i < RK_NC; ++i) {
+                    const double e = en[i] / es[i];
+                    esum = fma(e, e, esum);
+                }
             }
             const double error_norm = rms8(esum);
             // one pow for the accept and the reject controller (rk.py:155-170): divergent branches
