@@ -256,3 +256,28 @@ def test_kerr_queued_equals_parked_kernel(native, monkeypatch):
     for x, y in zip(res["1"], res["0"]):
         assert bits_equal(x, y)
     assert np.isfinite(res["1"][0]).sum() > 0.9 * H * W
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 127, 129, 4097])
+def test_kerr_queue_edge_sizes(native, oracle, monkeypatch, n):
+    """Batch sizes around the warp / CTA / queue-chunk boundaries, with invalid rays (alpha = 0)
+    at the chunk edges: the queued kernel terminates, equals the parked schedule bit for bit and
+    the oracle's classification."""
+    m = _kerr(1.0, 0.7)
+    rng = np.random.default_rng(n)
+    alpha = rng.uniform(0.01, 0.4, n)
+    alpha[:: 32] = 0.0                     # initial conditions fail: status 0 without stepping
+    if n > 40:
+        alpha[31:40] = 0.0
+    theta = rng.uniform(-np.pi, np.pi, n)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("LP_KERR_QUEUE", mode)
+        fa = np.empty(n)
+        w = np.empty(n, dtype=np.int64)
+        m.trace_rays_batch(30.0, alpha, theta, 1.3, None, fa, w)
+        res[mode] = (fa, w)
+    assert bits_equal(res["1"][0], res["0"][0]) and np.array_equal(res["1"][1], res["0"][1])
+    fa_o, w_o, st_o, _ = oracle.kerr_trace_rays_batch(1.0, 0.7, 30.0, alpha, theta, 1.3)
+    assert np.array_equal(np.isfinite(res["1"][0]), np.isfinite(fa_o))
+    assert np.array_equal(res["1"][1], w_o)
