@@ -181,7 +181,7 @@ class Schwarzschild(Metric):
 class Kerr(Metric):
     """Rotating black hole in Boyer-Lindquist coordinates, spin ``a`` with ``|a| <= M``
     (reference: metrics.py:840-1132).  Ray tracing (``trace_ray``, ``trace_rays_batch``) runs in
-    the CUDA kernel lp_kerr_kernel (csrc/lp_kerr.cu: the reference's Dormand-Prince 4(5)
+    the CUDA kernel lp_kerr_queued_kernel (csrc/lp_kerr.cu: the reference's Dormand-Prince 4(5)
     integrator on the reduced 5-D Hamiltonian state); the closed-form helpers are host
     arithmetic."""
 
