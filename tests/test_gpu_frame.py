@@ -213,6 +213,48 @@ def test_frame_symmetry_4k(native):
     assert abs(s["sum_steps"] - 459558513) <= 5000 and s["max_steps"] >= 200
 
 
+def test_frame_8k_config4_properties(native):
+    """BASELINE config 4 at its full size (7680x4320, 33 177 600 rays), through properties that
+    need no oracle: uneven row tiles (what 2 / 4 / 8 GPUs render) concatenate to the one-launch
+    frame bit for bit; the lookups are mirror images at psi = 0; every ray is classified; the
+    shadow's pixel count scales with the pixel area of the 4K frame's (same field of view)."""
+    import torch
+    from light_path_tracer_b200 import _device as dev
+    il = _il()
+    H, W = 4320, 7680
+    vfov = np.radians(40.0)
+    fov = (2 * np.arctan(np.tan(vfov / 2) * W / H), vfov)
+    metric = _metric(1.0)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    src = torch.rand(H, W, 3, device="cuda", generator=g)
+    full = il.render_frame(src, fov, 100.0, metric)
+    for parts in (2, 8):
+        bounds = [H * k // parts for k in range(parts + 1)]
+        out = torch.empty_like(full)
+        for k in range(parts):
+            il.render_frame(src, fov, 100.0, metric, rows=(bounds[k], bounds[k + 1] - bounds[k]),
+                            out=out[bounds[k]:bounds[k + 1]])
+        assert torch.equal(out, full), parts
+    bounds = [0, 1, 1000, 1001, 3333, H]                     # ragged tiles incl. single rows
+    out = torch.empty_like(full)
+    for k in range(len(bounds) - 1):
+        il.render_frame(src, fov, 100.0, metric, rows=(bounds[k], bounds[k + 1] - bounds[k]),
+                        out=out[bounds[k]:bounds[k + 1]])
+    assert torch.equal(out, full)
+    del out, full
+    stats = dev.new_stats()
+    a = il.build_alpha_lookup((H, W), fov, device=True)
+    fa, w = metric.trace_alpha_table(a, 100.0, stats=stats)
+    fa_i = fa.view(torch.int32)
+    assert torch.equal(fa_i[1:], fa_i[1:].flip(0)) and torch.equal(fa_i[:, 1:], fa_i[:, 1:].flip(1))
+    assert torch.equal(w.view(torch.int16)[1:], w.view(torch.int16)[1:].flip(0))
+    s = dev.read_stats(stats)
+    assert s["n_rays"] == H * W and s["n_invalid"] == 1
+    assert s["n_escaped"] + s["n_captured"] + s["n_invalid"] == H * W
+    assert abs(s["n_captured"] / 4.0 - 73368) < 0.01 * 73368   # 4K frame: 73 368 captured (SURVEY App. A)
+    assert int(torch.isnan(fa).sum().item()) == s["n_captured"] + s["n_invalid"]
+
+
 @pytest.mark.parametrize("H,W,r_obs,psi", [(2160, 3840, 100.0, (0.0, 0.0)), (2160, 3840, 15.0, (0.05, -0.1)),
                                            (1080, 1920, 1000.0, (0.0, 0.0))])
 def test_hybrid_frame_equals_strict_frame(native, H, W, r_obs, psi):
