@@ -255,6 +255,42 @@ def test_frame_8k_config4_properties(native):
     assert int(torch.isnan(fa).sum().item()) == s["n_captured"] + s["n_invalid"]
 
 
+def test_sweep_512_config5_properties(native):
+    """BASELINE config 5 at its full size (512 frames of 1024x1024: 32 distances x 16 camera
+    pitches, dist.sweep_grid), through properties that need no oracle: every ray of every frame
+    is classified; for a fixed pitch the visible shadow shrinks with the distance (same centre,
+    smaller disc); the lookups of pitch +p and -p are row-mirrored images bit for bit; and the
+    round-robin frame shards of 8 ranks cover the sweep exactly once."""
+    import torch
+    from light_path_tracer_b200 import _device as dev, dist as lpdist
+    il = _il()
+    H = W = 1024
+    vfov = np.radians(40.0)
+    fov = (2 * np.arctan(np.tan(vfov / 2) * W / H), vfov)
+    metric = _metric(1.0)
+    params = lpdist.sweep_grid()
+    assert len(params) == 512
+    shards = [lpdist.frame_shard(len(params), r, 8) for r in range(8)]
+    assert sorted(sum(shards, [])) == list(range(512)) and all(len(sh) == 64 for sh in shards)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    pipe = il.LensPipeline(torch.rand(H, W, 3, device="cuda", generator=g), 40.0, metric)
+    out = torch.empty(H, W, 3, device="cuda")
+    captured = np.zeros((32, 16), dtype=np.int64)
+    for k, (r_obs, psi) in enumerate(params):
+        stats = dev.new_stats()
+        pipe.render(r_obs, psi=psi, stats=stats, out=out)
+        s = dev.read_stats(stats)
+        assert s["n_rays"] == H * W and s["n_escaped"] + s["n_captured"] + s["n_invalid"] == H * W, k
+        captured[k // 16, k % 16] = s["n_captured"]
+    assert (np.diff(captured, axis=0) <= 0).all(), "the visible shadow must shrink with r_obs"
+    assert captured[0].min() > 50 * captured[-1].max() > 0
+    for r_obs, (p, _) in (params[3], params[16 * 13 + 1], params[16 * 31 + 6]):
+        fa_p, w_p = metric.trace_alpha_table(il.build_alpha_lookup((H, W), fov, psi=(p, 0.0), device=True), r_obs)
+        fa_m, w_m = metric.trace_alpha_table(il.build_alpha_lookup((H, W), fov, psi=(-p, 0.0), device=True), r_obs)
+        assert torch.equal(fa_p.view(torch.int32)[1:], fa_m.view(torch.int32)[1:].flip(0))
+        assert torch.equal(w_p.view(torch.int16)[1:], w_m.view(torch.int16)[1:].flip(0))
+
+
 @pytest.mark.parametrize("H,W,r_obs,psi", [(2160, 3840, 100.0, (0.0, 0.0)), (2160, 3840, 15.0, (0.05, -0.1)),
                                            (1080, 1920, 1000.0, (0.0, 0.0))])
 def test_hybrid_frame_equals_strict_frame(native, H, W, r_obs, psi):
