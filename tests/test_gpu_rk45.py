@@ -193,3 +193,43 @@ def test_kerr_generic_path_golden(native, golden, oracle):
     # several rays in one launch (plot_trajectories) and main.main(metric=Kerr)
     res = gt.trace_paths(Kerr(1.0, 0.9), 50.0, np.radians([3.0, 10.0]))
     assert [o for _, o in res] == ["captured", "escaped"]
+
+
+def test_config3_4k_generic_vs_binet(native):
+    """BASELINE config 3 at its full size (the generic 8-D RK45 integrator on every pixel of the
+    3840x2160 alpha table), checked against the INDEPENDENT Binet RK4 tracer on the same rays —
+    two different integrators of the same geodesics: escaped / captured must agree for every
+    pixel outside a 1e-6 band around the critical angle, and the number of half orbits
+    floor(|phi_f| / pi) wherever phi_f is not within 1e-4 of a multiple of pi (RK4 with
+    h = 0.05 carries ~1e-6 of phase error)."""
+    import torch
+    from light_path_tracer_b200 import image_lens as il
+    gt = _gt()
+    metric = _metric(1.0)
+    H, W = 2160, 3840
+    vfov = np.radians(40.0)
+    fov = (2 * np.arctan(np.tan(vfov / 2) * W / H), vfov)
+    a32 = il.build_alpha_lookup((H, W), fov, device=True)
+    status = torch.empty((H, W), dtype=torch.int8, device="cuda")
+    fa, w = metric.trace_alpha_table(a32, 100.0, status=status)
+    state, lam, outcome, nsteps = gt.trace_rays(metric, 100.0, a32.double())
+    ac = float(metric.alpha_crit(100.0))
+    clear = (a32.double() - ac).abs() > 1e-6 * ac
+    # the centre pixel (alpha = 0, a radial ray): the generic path captures it
+    # (geodesic_tracer.py:153-172 table, "0 deg captured"), the Binet fast path reports it
+    # invalid (b = 0, metrics.py:57-58)
+    valid = status != 0
+    assert int((~valid).sum().item()) == 1 and int((outcome == 0).sum().item()) == 0
+    assert int(outcome[~valid].item()) == -1
+    assert torch.equal(outcome[clear & valid], status[clear & valid])
+    assert int((~clear).sum().item()) < 64
+    phi = state[..., 3].abs()
+    frac = torch.remainder(phi / np.pi, 1.0)
+    safe = clear & valid & (frac > 1e-4) & (frac < 1 - 1e-4)
+    nh = torch.floor(phi / np.pi).to(torch.int64)
+    assert torch.equal(nh[safe], w.view(torch.int16).to(torch.int64)[safe])
+    assert int(safe.sum().item()) > 0.999 * H * W
+    esc = outcome == 1
+    r_f = state[..., 1][esc]
+    assert float((r_f - 200.0).abs().max().item()) < 1e-6            # terminal event at 2 r_obs
+    assert int(nsteps[..., 0].min().item()) >= 1 and int(nsteps[..., 1].max().item()) < 20000
