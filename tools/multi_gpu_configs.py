@@ -80,6 +80,14 @@ if world > 1:
     frame = rs.render_pipelined(100.0, dst=0, bands=4)
     full = il.render_frame(src, rs.pipe.fov, 100.0, metric) if rank == 0 else None
     out["bit_identical_to_single_gpu_frame"] = bool(torch.equal(frame, full)) if rank == 0 else None
+    # every rank's kernel stores its tile straight into rank 0's frame over NVLink (PeerFrame)
+    try:
+        pf = lpdist.PeerFrame(H, (W, 3), torch.float32, src.device, dst=0)
+        out["bands_peer"] = timed(lambda: rs.render_peer(100.0, frame=pf), args.reps)
+        got = rs.render_peer(100.0, frame=pf)
+        out["peer_bit_identical"] = bool(torch.equal(got, full)) if rank == 0 else None
+    except Exception as exc:                      # symmetric memory unavailable on this box
+        out["peer_error"] = repr(exc)[:200]
 if rank == 0:
     best = min(v for k, v in out.items() if k.startswith("bands"))
     print(json.dumps({"config": "4: 7680x4320 row-sharded x%d, gather to rank 0" % world, "ms_per_frame": out,
