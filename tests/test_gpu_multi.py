@@ -45,6 +45,14 @@ def _worker(rank, world, port, q):
         if rank == 0:
             res = {"gather": bool(torch.equal(a, full)), "bands": bool(torch.equal(b, full)),
                    "peer": (bool(torch.equal(c, full)) if peer_ok is True else peer_ok)}
+        # the auto path (peer stores, else band gather), twice: the second call reuses the mapping
+        d1 = rs.render_to_root(30.0, psi=(0.05, -0.02), dst=0)
+        d2 = rs.render_to_root(30.0, psi=(0.05, -0.02), dst=0)
+        if rank == 0:
+            res["to_root"] = bool(torch.equal(d1, full)) and bool(torch.equal(d2, full))
+            res["to_root_mode"] = rs._root_mode
+        else:
+            res["to_root"] = (d1 is None and d2 is None)
         every = rs.render(30.0, psi=(0.05, -0.02), dst=None)      # all_gather: every rank gets the frame
         res["all"] = bool(torch.equal(every, full))
         # host image in / host tile out with the upload sharded over the ranks
@@ -76,4 +84,6 @@ def test_two_rank_frame_bit_identical(native):
         assert p.exitcode == 0
     assert results[0]["gather"] and results[0]["bands"] and results[0]["all"] and results[1]["all"]
     assert results[0]["sharded_host"] and results[1]["sharded_host"]
+    assert results[0]["to_root"] and results[1]["to_root"]
+    assert results[0]["to_root_mode"] in ("peer", "bands")
     assert results[0]["peer"] is True, results[0]["peer"]
