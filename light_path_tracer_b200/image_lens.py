@@ -401,12 +401,13 @@ class LensPipeline:
         return render_frame(self.src, self.fov, r_obs, self.metric, psi=psi, rows=rows, stats=stats,
                             flags=flags, out=out)
 
-    def capture_sweep(self, params, out, flags=dev.TRACE_HYBRID):
+    def capture_sweep(self, params, out, flags=dev.TRACE_HYBRID, lanes=2):
         """Capture a whole parameter sweep — ``params`` = [(r_obs, psi), ...], frame j written to
         ``out[j]`` — in ONE CUDA graph and return it (``graph.replay()`` re-renders the sweep).
         Small frames are launch-bound when issued one by one from Python (a 1024x1024 frame is
-        ~0.11 ms of kernel time); the graph replays the launches back to back with the per-frame
-        constants baked in."""
+        ~0.11 ms of kernel time); the graph replays the launches with the per-frame constants
+        baked in, as ``lanes`` independent chains (frame j on chain j % lanes) so that one frame's
+        last CTAs share the SMs with the next frame's first ones instead of draining alone."""
         t = self._t
         if len(params) != int(out.shape[0]):
             raise ValueError("out must hold one frame per sweep point")
@@ -417,9 +418,21 @@ class LensPipeline:
                 self.render(r_obs, psi=psi, flags=flags, out=out[j])
         t.cuda.current_stream().wait_stream(side)
         graph = t.cuda.CUDAGraph()
+        lanes = max(1, min(int(lanes), len(params)))
         with t.cuda.graph(graph):
-            for j, (r_obs, psi) in enumerate(params):
-                self.render(r_obs, psi=psi, flags=flags, out=out[j])
+            if lanes == 1:
+                for j, (r_obs, psi) in enumerate(params):
+                    self.render(r_obs, psi=psi, flags=flags, out=out[j])
+            else:
+                cur = t.cuda.current_stream()
+                chains = [t.cuda.Stream(device=self.src.device) for _ in range(lanes)]
+                for st in chains:                         # fork
+                    st.wait_stream(cur)
+                for j, (r_obs, psi) in enumerate(params):
+                    with t.cuda.stream(chains[j % lanes]):
+                        self.render(r_obs, psi=psi, flags=flags, out=out[j])
+                for st in chains:                         # join
+                    cur.wait_stream(st)
         return graph
 
 
