@@ -167,8 +167,8 @@ class ShardedHostFrames:
     its own PCIe link, one NCCL all-gather over NVLink assembles the replicated source on every
     GPU (the remap may sample any source pixel), the fused kernel renders the rank's tile, the
     tile goes back to (pinned) host memory.  PCIe carries 1/N of the source per GPU instead of
-    all of it; two slots on two streams overlap one frame's upload with the previous frame's
-    download, as image_lens.HostFramePipeline does on one GPU.  Needs equal row tiles."""
+    all of it; ``depth`` slots on their own streams overlap one frame's upload with the previous
+    frame's download, as image_lens.HostFramePipeline does on one GPU.  Needs equal row tiles."""
 
     def __init__(self, shape, dtype, vertical_fov=None, metric=None, depth=3, group=None):
         import torch
