@@ -761,7 +761,7 @@ lp_kerr_queued_kernel(const KerrArgs a, const CamConsts cam)
 }
 
 // LP_KERR_FAST=1 selects the approximate-reciprocal right-hand side (it was 2.7x faster than the
-// first exact build; the exact build over shared reciprocals has closed that gap).  NOT the default: with
+// first exact build; against the exact build over shared reciprocals: 47 vs 51 ms).  NOT the default: with
 // the tight axis_refine tolerances (rtol 1e-8) the error norm is a 9-digit cancellation, a few ulp
 // in the stages move the step sizes by ~1e-8, and the reference's LINEAR interpolation at the exit
 // radius (metrics.py:533-548, an O(h^2) error that depends on where the last step falls) turns
