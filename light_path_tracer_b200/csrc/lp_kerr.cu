@@ -350,6 +350,78 @@ __device__ __forceinline__ double pixel_theta(const CamConsts &cam, int row, int
     return atan2(vx * cam.ex0 + vy * cam.ex1 + vz * cam.ex2, vx * cam.ey0 + vy * cam.ey1 + vz * cam.ey2);
 }
 
+// One trip of the reference's `for _step in range(max_steps)` (metrics.py:451-566) for one lane: the
+// loop guards, one Dormand-Prince attempt, the controller, the exit events.  done: 0 running,
+// 1 finished -> extract the final direction, 2 invalid (status 0).
+template <bool EXACT>
+__device__ __forceinline__ void kerr_trip(double (&state)[5], double (&k1)[5], double p_t, double p_phi,
+                                          double M, double sp, double r_floor, double r_capture, double r_escape,
+                                          double lambda_max, double h_min, double atol, double rtol,
+                                          double &lam, double &h, int &accepted, int &attempts, int &iters,
+                                          int &done, int &event_status)
+{
+    done = 0;
+    event_status = 2;
+    if (iters >= 200000 || lam >= lambda_max) {
+        done = 1;
+    } else {
+        iters++;
+        const double remaining = lambda_max - lam;
+        if (h > remaining) h = remaining;
+        if (h <= 0.0) {
+            done = 1;
+        } else {
+            attempts++;
+            double k3[5], k4[5], k5[5], k6[5], k7[5], nxt[5];
+            kerr_dp_stages<EXACT>(state, k1, h, p_t, p_phi, M, sp, r_floor, k3, k4, k5, k6, k7, nxt);
+
+            if (!finite5(nxt) || nxt[0] <= 0.0) {                        // metrics.py:498-503
+                h *= 0.25;
+                if (h < h_min) done = 2;
+            } else {
+                const double err_sq = kerr_err_sq(state, nxt, k1, k3, k4, k5, k6, k7, h, atol, rtol);
+                const double err_norm = __dsqrt_rn(err_sq / 5.0);
+                // 0.9 * err_norm ** -0.2 feeds both the reject (metrics.py:517) and the accept
+                // (metrics.py:562) controller: one pow for the whole warp instead of one per
+                // divergent branch
+                const double pow_term = 0.9 * pow(err_norm, -0.2);
+                if (err_norm > 1.0) {                                    // reject, metrics.py:516-522
+                    const double factor = fmax(0.2, pow_term);
+                    h *= factor;
+                    if (h < h_min) done = 2;
+                } else {
+                    accepted++;
+                    const double r_prev = state[0], r_next = nxt[0];
+                    const bool cap = (r_prev > r_capture && r_next <= r_capture);
+                    const bool esc = !cap && (r_prev < r_escape && r_next >= r_escape);
+                    if (cap || esc) {                                    // metrics.py:528-550
+                        const double target = cap ? r_capture : r_escape;
+                        const double denom = r_next - r_prev;
+                        double frac = (denom == 0.0) ? 1.0 : (target - r_prev) / denom;
+                        frac = clip_scalar(frac, 0.0, 1.0);
+#pragma unroll
+                        for (int i = 0; i < 5; ++i) state[i] = state[i] + frac * (nxt[i] - state[i]);
+                        lam += frac * h;
+                        event_status = cap ? -1 : 1;
+                        done = 1;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 5; ++i) { state[i] = nxt[i]; k1[i] = k7[i]; }
+                        lam += h;
+                        if (!finite5(state)) {
+                            done = 2;
+                        } else if (err_norm < 1e-10) {
+                            h *= 5.0;
+                        } else {
+                            h *= fmin(5.0, pow_term);
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
 template <bool EXACT, int MINB>
 __global__ void __launch_bounds__(KERR_BLOCK, MINB)
 lp_kerr_kernel(const KerrArgs a, const CamConsts cam)
@@ -442,67 +514,9 @@ lp_kerr_kernel(const KerrArgs a, const CamConsts cam)
         if (!active) continue;
 
         // ---------------- one trip of the reference's `for _step in range(max_steps)` ----------------
-        int done = 0;            // 0 running, 1 finished -> extract angle, 2 invalid (status 0)
-        int event_status = 2;
-        if (iters >= 200000 || lam >= lambda_max) {
-            done = 1;
-        } else {
-            iters++;
-            const double remaining = lambda_max - lam;
-            if (h > remaining) h = remaining;
-            if (h <= 0.0) {
-                done = 1;
-            } else {
-                attempts++;
-                double k3[5], k4[5], k5[5], k6[5], k7[5], nxt[5];
-                kerr_dp_stages<EXACT>(state, k1, h, p_t, p_phi, M, sp, r_floor, k3, k4, k5, k6, k7, nxt);
-
-                if (!finite5(nxt) || nxt[0] <= 0.0) {                        // metrics.py:498-503
-                    h *= 0.25;
-                    if (h < h_min) done = 2;
-                } else {
-                    const double err_sq = kerr_err_sq(state, nxt, k1, k3, k4, k5, k6, k7, h, atol, rtol);
-                    const double err_norm = __dsqrt_rn(err_sq / 5.0);
-                    // 0.9 * err_norm ** -0.2 feeds both the reject (metrics.py:517) and the accept
-                    // (metrics.py:562) controller: one pow for the whole warp instead of one per
-                    // divergent branch
-                    const double pow_term = 0.9 * pow(err_norm, -0.2);
-                    if (err_norm > 1.0) {                                    // reject, metrics.py:516-522
-                        const double factor = fmax(0.2, pow_term);
-                        h *= factor;
-                        if (h < h_min) done = 2;
-                    } else {
-                        accepted++;
-                        const double r_prev = state[0], r_next = nxt[0];
-                        const bool cap = (r_prev > r_capture && r_next <= r_capture);
-                        const bool esc = !cap && (r_prev < r_escape && r_next >= r_escape);
-                        if (cap || esc) {                                    // metrics.py:528-550
-                            const double target = cap ? r_capture : r_escape;
-                            const double denom = r_next - r_prev;
-                            double frac = (denom == 0.0) ? 1.0 : (target - r_prev) / denom;
-                            frac = clip_scalar(frac, 0.0, 1.0);
-#pragma unroll
-                            for (int i = 0; i < 5; ++i) state[i] = state[i] + frac * (nxt[i] - state[i]);
-                            lam += frac * h;
-                            event_status = cap ? -1 : 1;
-                            done = 1;
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 5; ++i) { state[i] = nxt[i]; k1[i] = k7[i]; }
-                            lam += h;
-                            if (!finite5(state)) {
-                                done = 2;
-                            } else if (err_norm < 1e-10) {
-                                h *= 5.0;
-                            } else {
-                                h *= fmin(5.0, pow_term);
-                            }
-                        }
-                    }
-                }
-            }
-        }
-
+        int done, event_status;
+        kerr_trip<EXACT>(state, k1, p_t, p_phi, M, sp, r_floor, r_capture, r_escape, lambda_max, h_min, atol, rtol,
+                         lam, h, accepted, attempts, iters, done, event_status);
         if (done) {          // park the lane: its result is produced in the next flush phase
             pending = done;
             pend_event = event_status;
@@ -696,62 +710,9 @@ lp_kerr_queued_kernel(const KerrArgs a, const CamConsts cam)
         if (!active) continue;
 
         // ---------------- one trip of the reference's `for _step in range(max_steps)` ----------------
-        int done = 0;            // 0 running, 1 finished -> extract angle, 2 invalid (status 0)
-        int event_status = 2;
-        if (iters >= 200000 || lam >= lambda_max) {
-            done = 1;
-        } else {
-            iters++;
-            const double remaining = lambda_max - lam;
-            if (h > remaining) h = remaining;
-            if (h <= 0.0) {
-                done = 1;
-            } else {
-                attempts++;
-                double k3[5], k4[5], k5[5], k6[5], k7[5], nxt[5];
-                kerr_dp_stages<EXACT>(state, k1, h, p_t, p_phi, M, sp, r_floor, k3, k4, k5, k6, k7, nxt);
-
-                if (!finite5(nxt) || nxt[0] <= 0.0) {                        // metrics.py:498-503
-                    h *= 0.25;
-                    if (h < h_min) done = 2;
-                } else {
-                    const double err_sq = kerr_err_sq(state, nxt, k1, k3, k4, k5, k6, k7, h, atol, rtol);
-                    const double err_norm = __dsqrt_rn(err_sq / 5.0);
-                    const double pow_term = 0.9 * pow(err_norm, -0.2);       // metrics.py:517, :562
-                    if (err_norm > 1.0) {                                    // reject, metrics.py:516-522
-                        h *= fmax(0.2, pow_term);
-                        if (h < h_min) done = 2;
-                    } else {
-                        accepted++;
-                        const double r_prev = state[0], r_next = nxt[0];
-                        const bool cap = (r_prev > r_capture && r_next <= r_capture);
-                        const bool esc = !cap && (r_prev < r_escape && r_next >= r_escape);
-                        if (cap || esc) {                                    // metrics.py:528-550
-                            const double target = cap ? r_capture : r_escape;
-                            const double denom = r_next - r_prev;
-                            double frac = (denom == 0.0) ? 1.0 : (target - r_prev) / denom;
-                            frac = clip_scalar(frac, 0.0, 1.0);
-#pragma unroll
-                            for (int i = 0; i < 5; ++i) state[i] = state[i] + frac * (nxt[i] - state[i]);
-                            lam += frac * h;
-                            event_status = cap ? -1 : 1;
-                            done = 1;
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 5; ++i) { state[i] = nxt[i]; k1[i] = k7[i]; }
-                            lam += h;
-                            if (!finite5(state)) {
-                                done = 2;
-                            } else if (err_norm < 1e-10) {
-                                h *= 5.0;
-                            } else {
-                                h *= fmin(5.0, pow_term);
-                            }
-                        }
-                    }
-                }
-            }
-        }
+        int done, event_status;
+        kerr_trip<EXACT>(state, k1, p_t, p_phi, M, sp, r_floor, r_capture, r_escape, lambda_max, h_min, atol, rtol,
+                         lam, h, accepted, attempts, iters, done, event_status);
         if (done) {
             pending = done;
             pend_event = event_status;
