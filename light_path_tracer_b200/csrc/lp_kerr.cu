@@ -350,6 +350,41 @@ __device__ __forceinline__ double pixel_theta(const CamConsts &cam, int row, int
     return atan2(vx * cam.ex0 + vy * cam.ex1 + vz * cam.ex2, vx * cam.ey0 + vy * cam.ey1 + vz * cam.ey2);
 }
 
+// Viewing angle, screen angle and axis_refine flag of ray `ray`: from the caller's arrays, or from
+// the float32 alpha table and the pixel position (image_lens.py:194-208, :247).
+__device__ __forceinline__ void kerr_load_ray(const KerrArgs &a, const CamConsts &cam, long long ray,
+                                              double &alpha, double &theta, bool &refine)
+{
+    if (a.frame_mode) {
+        int row, col;
+        pixel_row_col(ray, a.n, cam.width, a.row0, row, col);
+        alpha = (double)__ldg(a.alpha32 + ray);
+        theta = pixel_theta(cam, row, col);
+        refine = a.refine_cols ? (__ldg(a.refine_cols + col) != 0) : false;
+    } else {
+        alpha = __ldg(a.alphas + ray);
+        theta = __ldg(a.thetas + ray);
+        refine = a.refine ? (__ldg(a.refine + ray) != 0) : false;
+    }
+}
+
+__device__ __forceinline__ void kerr_store_result(const KerrArgs &a, long long idx, int status, double fa,
+                                                  long long nh, int accepted, int attempts)
+{
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    const double fa_out = (status == 1) ? fa : qnan;                         // metrics.py:678
+    if (a.wide) {
+        ((double *)a.out_fa)[idx] = fa_out;
+        ((long long *)a.out_w)[idx] = nh;
+    } else {
+        ((float *)a.out_fa)[idx] = (float)fa_out;                            // image_lens.py:261
+        const long long c = nh < 0 ? 0 : (nh > 65535 ? 65535 : nh);          // image_lens.py:262
+        ((unsigned short *)a.out_w)[idx] = (unsigned short)c;
+    }
+    if (a.out_status) a.out_status[idx] = (int8_t)status;
+    if (a.out_steps) { a.out_steps[2 * idx] = accepted; a.out_steps[2 * idx + 1] = attempts; }
+}
+
 // One trip of the reference's `for _step in range(max_steps)` (metrics.py:451-566) for one lane: the
 // loop guards, one Dormand-Prince attempt, the controller, the exit events.  done: 0 running,
 // 1 finished -> extract the final direction, 2 invalid (status 0).
@@ -457,17 +492,7 @@ lp_kerr_kernel(const KerrArgs a, const CamConsts cam)
             long long nh = 0;
             int status = 0;
             if (pending == 1) status = kerr_extract_angle(state, p_t, p_phi, M, sp, r_capture, pend_event, fa, nh);
-            const double fa_out = (status == 1) ? fa : qnan;                 // metrics.py:678
-            if (a.wide) {
-                ((double *)a.out_fa)[idx] = fa_out;
-                ((long long *)a.out_w)[idx] = nh;
-            } else {
-                ((float *)a.out_fa)[idx] = (float)fa_out;                    // image_lens.py:261
-                const long long c = nh < 0 ? 0 : (nh > 65535 ? 65535 : nh);  // image_lens.py:262
-                ((unsigned short *)a.out_w)[idx] = (unsigned short)c;
-            }
-            if (a.out_status) a.out_status[idx] = (int8_t)status;
-            if (a.out_steps) { a.out_steps[2 * idx] = accepted; a.out_steps[2 * idx + 1] = attempts; }
+            kerr_store_result(a, idx, status, fa, nh, accepted, attempts);
             pending = 0;
         }
         if (flush && !queue_empty) {
@@ -480,17 +505,7 @@ lp_kerr_kernel(const KerrArgs a, const CamConsts cam)
                 idx = ray;
                 double alpha, theta;
                 bool refine;
-                if (a.frame_mode) {
-                    int row, col;
-                    pixel_row_col(ray, a.n, cam.width, a.row0, row, col);
-                    alpha = (double)__ldg(a.alpha32 + ray);                 // image_lens.py:247
-                    theta = pixel_theta(cam, row, col);
-                    refine = a.refine_cols ? (__ldg(a.refine_cols + col) != 0) : false;
-                } else {
-                    alpha = __ldg(a.alphas + ray);
-                    theta = __ldg(a.thetas + ray);
-                    refine = a.refine ? (__ldg(a.refine + ray) != 0) : false;
-                }
+                kerr_load_ray(a, cam, ray, alpha, theta, refine);
                 atol = refine ? 1e-10 : 1e-8;                               // metrics.py:432-433
                 rtol = refine ? 1e-8 : 1e-6;
                 if (kerr_init(M, sp, a.r_obs, alpha, theta, a.theta_obs, a.sin_th_obs, a.cos_th_obs, state, p_t, p_phi)) {
@@ -500,10 +515,7 @@ lp_kerr_kernel(const KerrArgs a, const CamConsts cam)
                     accepted = 0; attempts = 0; iters = 0;
                     active = true;
                 } else {
-                    if (a.wide) { ((double *)a.out_fa)[idx] = qnan; ((long long *)a.out_w)[idx] = 0; }
-                    else { ((float *)a.out_fa)[idx] = (float)qnan; ((unsigned short *)a.out_w)[idx] = 0; }
-                    if (a.out_status) a.out_status[idx] = 0;
-                    if (a.out_steps) { a.out_steps[2 * idx] = 0; a.out_steps[2 * idx + 1] = 0; }
+                    kerr_store_result(a, idx, 0, qnan, 0, 0, 0);      // initial conditions invalid: status 0
                 }
             }
         }
@@ -545,23 +557,6 @@ struct KerrWarpQueues {
     int out_accepted[32], out_attempts[32], out_code[32];   // code = done | (event_status + 1) << 2
     int in_flag[32];                                        // bit 0 valid, bit 1 axis_refine
 };
-
-__device__ __forceinline__ void kerr_store_result(const KerrArgs &a, long long idx, int status, double fa,
-                                                  long long nh, int accepted, int attempts)
-{
-    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-    const double fa_out = (status == 1) ? fa : qnan;                         // metrics.py:678
-    if (a.wide) {
-        ((double *)a.out_fa)[idx] = fa_out;
-        ((long long *)a.out_w)[idx] = nh;
-    } else {
-        ((float *)a.out_fa)[idx] = (float)fa_out;                            // image_lens.py:261
-        const long long c = nh < 0 ? 0 : (nh > 65535 ? 65535 : nh);          // image_lens.py:262
-        ((unsigned short *)a.out_w)[idx] = (unsigned short)c;
-    }
-    if (a.out_status) a.out_status[idx] = (int8_t)status;
-    if (a.out_steps) { a.out_steps[2 * idx] = accepted; a.out_steps[2 * idx + 1] = attempts; }
-}
 
 template <bool EXACT, int MINB>
 __global__ void __launch_bounds__(KERR_BLOCK, MINB)
@@ -651,17 +646,7 @@ lp_kerr_queued_kernel(const KerrArgs a, const CamConsts cam)
                 if (ray < a.n) {
                     double alpha, theta;
                     bool refine;
-                    if (a.frame_mode) {
-                        int row, col;
-                        pixel_row_col(ray, a.n, cam.width, a.row0, row, col);
-                        alpha = (double)__ldg(a.alpha32 + ray);             // image_lens.py:247
-                        theta = pixel_theta(cam, row, col);
-                        refine = a.refine_cols ? (__ldg(a.refine_cols + col) != 0) : false;
-                    } else {
-                        alpha = __ldg(a.alphas + ray);
-                        theta = __ldg(a.thetas + ray);
-                        refine = a.refine ? (__ldg(a.refine + ray) != 0) : false;
-                    }
+                    kerr_load_ray(a, cam, ray, alpha, theta, refine);
                     double s0[5], kk[5], i_p_t, i_p_phi;
                     const bool ok = kerr_init(M, sp, a.r_obs, alpha, theta, a.theta_obs, a.sin_th_obs, a.cos_th_obs,
                                               s0, i_p_t, i_p_phi);
