@@ -76,6 +76,29 @@ def _worker(rank, world, port, height, q):
                     ok = ok and torch.equal(frame, expect)
                 else:
                     ok = ok and frame is None
+        # RowShardedRenderer.render_to_root: path selection and caching with a stub renderer (the
+        # real one needs a GPU): no CUDA -> no peer mapping -> pipelined bands when the tiles are
+        # equal, whole-tile gather otherwise; the second call reuses the cached choice and buffers
+        import types
+        from light_path_tracer_b200.dist import RowShardedRenderer
+        src = torch.zeros(height, 6, 3)
+        rs = RowShardedRenderer.__new__(RowShardedRenderer)     # LensPipeline itself refuses to exist without CUDA
+        rs.pipe = types.SimpleNamespace(src=src, height=height, width=6)
+        rs.group, rs.world, rs.rank, rs.tiles = None, world, rank, row_tiles(height, world)
+
+        def stub_render(r_obs, psi=(0.0, 0.0), rows=None, stats=None, flags=None, out=None):
+            r0, n = rows
+            val = (torch.arange(r0, r0 + n, dtype=torch.float32) + float(r_obs)).reshape(n, 1, 1).expand(n, 6, 3)
+            if out is None:
+                return val.contiguous()
+            out.copy_(val)
+            return out
+        rs.pipe.render = stub_render
+        for r_obs in (1.0, 2.0):
+            frame = rs.render_to_root(r_obs, dst=0)
+            expect = (torch.arange(height, dtype=torch.float32) + r_obs).reshape(height, 1, 1).expand(height, 6, 3)
+            ok = ok and ((torch.equal(frame, expect)) if rank == 0 else (frame is None))
+        ok = ok and rs._root_mode == ("bands" if height % world == 0 else "tiles")
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
