@@ -386,14 +386,25 @@ def run_gpu(args):
         kerr = Kerr(M, 0.9)
         cam_k = dev.camera_vector((H, W), fov, (0.0, 0.0), il._psi_frame)
         t_kerr, _ = once(lambda: kerr.trace_alpha_table_2d(a32, cam_k, R_OBS, np.pi / 2))
+        # the same Kerr frame through the reference-facing call, which traces the top half only and
+        # mirrors it for an equatorial observer with psi_y = 0 (image_lens.py:236-240, :264-270)
+        try:
+            t_kerr_api, _ = once(lambda: il.precompute_final_alpha_lookup_2d(
+                a32, fov, kerr.alpha_crit(R_OBS), R_OBS, kerr, theta_obs=np.pi / 2, psi=(0.0, 0.0)))
+        except Exception as exc:                      # auxiliary figure only
+            t_kerr_api = None
+            sys.stderr.write("kerr API lookup skipped: %r\n" % (exc,))
         extra = {
             "config3_rk45_frame_4k": {"ms": t_rk45, "rays_per_s": H * W / t_rk45 * 1e3,
                                       "step_attempts_per_s": rk_attempts / t_rk45 * 1e3,
                                       "what": "geodesic_tracer.trace_ray semantics (scipy RK45, rtol 1e-8) for every "
                                               "pixel of the 3840x2160 alpha table, lp_rk45_kernel"},
             "kerr_lookup_4k": {"ms": t_kerr, "rays_per_s": H * W / t_kerr * 1e3,
+                               "ms_api_with_mirror": t_kerr_api,
                                "what": "Kerr a=0.9 M, equatorial observer: (alpha, theta) lookup of the full "
-                                       "3840x2160 frame without the top/bottom mirror, lp_kerr_kernel"},
+                                       "3840x2160 frame without the top/bottom mirror, lp_kerr_queued_kernel; "
+                                       "ms_api_with_mirror = image_lens.precompute_final_alpha_lookup_2d on the "
+                                       "same device-resident alpha table (top half traced, bottom mirrored)"},
             "e2e_u8_io": {"value": H * W / t_u8 * 1e3, "unit": "rays/s", "ms_per_frame": t_u8,
                           "h2d_bytes_per_step": int(src8_host.numel()), "d2h_bytes_per_step": int(out8[0].numel()),
                           "path": "as e2e, with the uint8 image boundary of image_lens.main (imread uint8 ... imsave "
