@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define LP_ABI_VERSION 1
+#define LP_ABI_VERSION 2
 
 /* ---- return codes ------------------------------------------------------- */
 #define LP_OK               0
@@ -45,7 +45,15 @@ extern "C" {
                                      reference's order (bit-identical u, w, phi)   */
 #define LP_TRACE_FUSED      1u    /* allow FMA contraction inside the RK4 step
                                      (faster, ulp-level different trajectories)     */
-#define LP_TRACE_NO_REPACK  2u    /* reserved                                        */
+#define LP_TRACE_REPACK     2u    /* lp_render_frame / lp_schw_trace_frame: force the lane
+                                     re-packing schedule (persistent warps; a lane whose ray has
+                                     left the integration band hands it to the warp's result
+                                     queue and takes the next prepared ray, so captured / escaped
+                                     rays stop wasting lanes).  Same results bit for bit.  Without
+                                     this flag (and without LP_TRACE_NO_REPACK) the library picks
+                                     the schedule per launch from the frame geometry (see
+                                     lp_render_schedule)                                     */
+#define LP_TRACE_NO_REPACK  32u   /* force the one-ray-per-thread schedule                   */
 #define LP_TRACE_HYBRID     4u    /* FMA-contracted loop for rays that finish within 12 rad
                                      of swept angle (240 RK4 steps at h = 0.05; they stay
                                      within 1e-11 of the strict result), strict re-trace of
@@ -58,6 +66,10 @@ extern "C" {
                                      shared memory and store them as 16-byte vectors (full
                                      sectors).  For tiles that live in a PEER GPU's memory
                                      (NVLink): ~1 % slower than plain stores into local HBM  */
+
+#define LP_RENDER_OUT_FRAME_ROWS 16u /* lp_render_frame_bands: `out` addresses frame row `row0` of a
+                                     FULL frame (row pitch = width*channels elements) and every pixel
+                                     is stored at its frame row, instead of into a compact tile       */
 
 /* ---- ray status codes (metrics.py:69, :125) ------------------------------ */
 #define LP_RAY_ESCAPED    1
@@ -201,6 +213,44 @@ int lp_render_frame(const void *src, int32_t src_dtype, int32_t channels,
                     int32_t render_loop_around, int32_t sampling,
                     void *out, float *out_fa32, uint16_t *out_w16,
                     lp_frame_stats *stats, uint32_t flags, void *stream);
+
+/* lp_render_frame over an INTERLEAVED set of rows (multi-GPU load balance: the black hole
+ * sits in the centre rows, so contiguous row tiles are unevenly expensive; rank g of G renders
+ * bands g, g+G, g+2G, ... of band_rows rows each).  Tile-local row r is frame row
+ *     row0 + (r / band_rows) * band_stride + (r % band_rows),        r in [0, rows)
+ * band_rows == 0 means contiguous rows (then this IS lp_render_frame).  out / out_fa32 /
+ * out_w16 are compact tiles of `rows` rows unless flags has LP_RENDER_OUT_FRAME_ROWS, in which
+ * case `out` (only) is frame-addressed: it points at frame row row0 of a full frame and must
+ * reach the tile's last frame row.  Replaces the same reference lines as lp_render_frame
+ * (image_lens.py:133-178, :296-397); the reference has no sharding. */
+int lp_render_frame_bands(const void *src, int32_t src_dtype, int32_t channels,
+                          const lp_camera *h_cam, int32_t row0, int32_t rows,
+                          int32_t band_rows, int32_t band_stride,
+                          double M, double R_S, double r_obs, double phi_max, double h_max,
+                          int32_t render_loop_around, int32_t sampling,
+                          void *out, float *out_fa32, uint16_t *out_w16,
+                          lp_frame_stats *stats, uint32_t flags, void *stream);
+
+/* Which schedule lp_render_frame would pick for this frame without LP_TRACE_REPACK /
+ * LP_TRACE_NO_REPACK: 1 = lane re-packing, 0 = one ray per thread.  Host arithmetic only. */
+int lp_render_schedule(const lp_camera *h_cam, int32_t row0, int32_t rows,
+                       double M, double R_S, double r_obs, int32_t *repack);
+
+/* ---- peer-memory completion flags (multi-GPU frame assembly) -------------
+ * Row tiles are stored by every rank's render kernel straight into the root GPU's frame
+ * through NVLink peer mappings; these two stream-ordered calls order "all tiles of frame e
+ * have landed" and "the root has consumed frame e" without a collective.  Flags are uint64
+ * epoch counters in (peer-mapped) device memory, only ever increased.
+ *   lp_peer_signal: after all prior work of `stream` has completed and its writes are visible
+ *                   system-wide, store `value` (release, system scope) to each of the n_flags
+ *                   device addresses in the HOST array h_flags (n_flags <= 16).
+ *   lp_peer_wait:   block `stream` until each of flags[0..n_flags) (local device memory) is
+ *                   >= value (acquire, system scope).  Gives up after timeout_ms (0 = 10 s)
+ *                   and then writes 1 to *timed_out (device int32, optional) so that a dead
+ *                   peer cannot hang the GPU. */
+int lp_peer_signal(uint64_t *const *h_flags, int32_t n_flags, uint64_t value, void *stream);
+int lp_peer_wait(const uint64_t *flags, int32_t n_flags, uint64_t value,
+                 uint32_t timeout_ms, int32_t *timed_out, void *stream);
 
 /* ---- kernel (3): shadow classification and frame reductions --------------- */
 

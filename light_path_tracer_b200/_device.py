@@ -1,7 +1,27 @@
 """Device plumbing shared by the reference-facing modules: host<->device staging through
 pinned memory, camera packing, frame-statistics decoding.  PyTorch is used for memory
-and streams only; all compute goes through the C ABI (``_lib.ext()``)."""
+and streams only; all compute goes through the C ABI (``_lib.ext()``).
+
+Host <-> device staging (the numpy-in / numpy-out drop-in calls, reference
+image_lens.py:480-505):
+
+* results come back in PINNED host memory: ``d2h`` copies the device tensor into a fresh pinned
+  block of torch's caching host allocator and returns a numpy view of it (kept alive by the
+  array's ``base``), so the DMA writes the caller's array directly — no second host copy, no
+  page faults on a fresh 100 MB allocation;
+* arrays that are already pinned (e.g. the alpha / final_alpha / winding tables this package
+  returned a moment ago) are uploaded straight from where they are;
+* pageable arrays are staged through a fresh pinned block in chunks, copied by a small thread
+  pool (numpy releases the GIL) while the previous chunks are already on the PCIe link.
+
+Every staging block is single-use: it is allocated per call and handed back to the caching host
+allocator, which does not reuse a block while a non_blocking copy recorded on it is in flight.
+Host->device staging is refused while a CUDA graph is being captured (the copy node would
+re-read whatever the block holds at replay time).
+"""
 import ctypes
+import os
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -13,9 +33,14 @@ H_MAX = 0.05     # metrics.py:833 (and :824 for the scalar path)
 TRACE_STRICT = 0
 TRACE_FUSED = 1
 RENDER_STAGED_STORES = 8   # lp_render_frame: 16-byte staged pixel stores (peer-memory tiles)
+TRACE_REPACK = 2            # force the lane re-packing schedule (lp_repack.cu)
+TRACE_NO_REPACK = 32        # force one ray per thread (default: chosen per launch from the geometry)
+RENDER_OUT_FRAME_ROWS = 16  # interleaved-band tile stored at its frame rows (peer frames)
 TRACE_HYBRID = 4   # FMA loop + strict re-trace of rays longer than 240 steps (lightpath.h)
 
-_pinned = {}
+_CHUNK_BYTES = 8 << 20          # staging granularity of large pageable arrays
+_THREADED_MIN_BYTES = 4 << 20   # below this one np.copyto is cheaper than the pool
+_pool = None
 
 
 def torch():
@@ -27,26 +52,71 @@ def device():
     return t.device("cuda", t.cuda.current_device())
 
 
-def pinned_buffer(tag, nbytes):
-    """Grow-only pinned staging buffer (uint8 tensor) per (tag, device)."""
+def _copy_pool():
+    global _pool
+    if _pool is None:
+        try:
+            n = len(os.sched_getaffinity(0))
+        except AttributeError:
+            n = os.cpu_count() or 1
+        _pool = ThreadPoolExecutor(max_workers=max(1, min(8, n)), thread_name_prefix="lp-stage")
+    return _pool
+
+
+def _pinned_empty(shape, dtype):
+    """Fresh pinned tensor from torch's caching host allocator (single-use staging block)."""
     t = torch()
-    key = (tag, t.cuda.current_device())
-    buf = _pinned.get(key)
-    if buf is None or buf.numel() < nbytes:
-        buf = t.empty(max(int(nbytes), 1 << 16), dtype=t.uint8, pin_memory=True)
-        _pinned[key] = buf
-    return buf
+    return t.empty(tuple(shape), dtype=dtype, pin_memory=True)
+
+
+def _is_pinned_array(arr):
+    """numpy array backed by page-locked memory (ours or the caller's)?"""
+    t = torch()
+    if not _NP2T:
+        _torch_dtype(np.float32)
+    if not (arr.flags.c_contiguous and arr.flags.writeable and arr.dtype in _NP2T):
+        return False
+    try:
+        return bool(t.from_numpy(arr).is_pinned())
+    except Exception:
+        return False
+
+
+def _chunks(nbytes):
+    n = max(1, (nbytes + _CHUNK_BYTES - 1) // _CHUNK_BYTES)
+    step = -(-nbytes // n)
+    step = (step + 4095) & ~4095
+    return [(o, min(o + step, nbytes)) for o in range(0, nbytes, step)]
 
 
 def h2d(arr, tag="h2d"):
-    """numpy array (any layout) -> contiguous CUDA tensor of the same dtype/shape."""
+    """numpy array (any layout) -> contiguous CUDA tensor of the same dtype/shape.
+    Stream-ordered on the current stream; does not synchronise."""
     t = torch()
     arr = np.asarray(arr)
+    tdt = _torch_dtype(arr.dtype)
     if arr.size == 0:
-        return t.empty(arr.shape, dtype=_torch_dtype(arr.dtype), device=device())
-    stage = pinned_buffer(tag, arr.nbytes)[:arr.nbytes].view(_torch_dtype(arr.dtype)).view(arr.shape)
-    np.copyto(stage.numpy(), arr)
-    return stage.to(device(), non_blocking=True)
+        return t.empty(arr.shape, dtype=tdt, device=device())
+    if t.cuda.is_current_stream_capturing():
+        raise RuntimeError("host->device staging inside CUDA graph capture: upload before capturing")
+    if _is_pinned_array(arr):
+        return t.from_numpy(arr).to(device(), non_blocking=True)
+    out = t.empty(arr.shape, dtype=tdt, device=device())
+    stage = _pinned_empty(arr.shape, tdt)
+    if arr.nbytes < _THREADED_MIN_BYTES or not arr.flags.c_contiguous:
+        np.copyto(stage.numpy(), arr)
+        out.copy_(stage, non_blocking=True)
+        return out
+    src_b = arr.reshape(-1).view(np.uint8)
+    stage_b = stage.view(-1).view(t.uint8)
+    out_b = out.view(-1).view(t.uint8)
+    stage_np = stage_b.numpy()
+    parts = _chunks(arr.nbytes)
+    futs = [_copy_pool().submit(np.copyto, stage_np[a:b], src_b[a:b]) for a, b in parts]
+    for (a, b), f in zip(parts, futs):       # chunk k is on the link while chunk k+1 is still being staged
+        f.result()
+        out_b[a:b].copy_(stage_b[a:b], non_blocking=True)
+    return out
 
 
 def d2h_into(tensor, out, tag="d2h"):
@@ -54,24 +124,60 @@ def d2h_into(tensor, out, tag="d2h"):
     t = torch()
     if tensor.numel() == 0:
         return
+    tensor = tensor.contiguous()
+    if tuple(out.shape) == tuple(tensor.shape) and out.dtype == _numpy_dtype(tensor.dtype) and _is_pinned_array(out):
+        t.from_numpy(out).copy_(tensor, non_blocking=True)
+        t.cuda.current_stream().synchronize()
+        return
+    stage = _pinned_empty(tensor.shape, tensor.dtype)
     nbytes = tensor.numel() * tensor.element_size()
-    stage = pinned_buffer(tag, nbytes)[:nbytes].view(tensor.dtype).view(tensor.shape)
-    stage.copy_(tensor, non_blocking=True)
-    t.cuda.current_stream().synchronize()
-    np.copyto(out, stage.numpy().reshape(out.shape), casting="same_kind")
+    direct = (out.flags.c_contiguous and tuple(out.shape) == tuple(tensor.shape)
+              and out.dtype == _numpy_dtype(tensor.dtype) and nbytes >= _THREADED_MIN_BYTES)
+    if not direct:
+        stage.copy_(tensor, non_blocking=True)
+        t.cuda.current_stream().synchronize()
+        np.copyto(out, stage.numpy().reshape(out.shape), casting="same_kind")
+        return
+    stage_b = stage.view(-1).view(t.uint8)
+    src_b = tensor.view(-1).view(t.uint8)
+    dst_b = out.reshape(-1).view(np.uint8)
+    stage_np = stage_b.numpy()
+    parts = _chunks(nbytes)
+    events = []
+    for a, b in parts:
+        stage_b[a:b].copy_(src_b[a:b], non_blocking=True)
+        ev = t.cuda.Event()
+        ev.record()
+        events.append(ev)
+    futs = []
+    for (a, b), ev in zip(parts, events):    # chunk k is copied out while chunk k+1 is still on the link
+        ev.synchronize()
+        futs.append(_copy_pool().submit(np.copyto, dst_b[a:b], stage_np[a:b]))
+    for f in futs:
+        f.result()
 
 
 def d2h(tensor, tag="d2h"):
-    out = np.empty(tuple(tensor.shape), dtype=_numpy_dtype(tensor.dtype))
-    d2h_into(tensor, out, tag)
-    return out
+    """CUDA tensor -> numpy array in pinned host memory (see the module docstring)."""
+    t = torch()
+    tensor = tensor.contiguous()
+    host = _pinned_empty(tensor.shape, tensor.dtype)
+    if tensor.numel():
+        host.copy_(tensor, non_blocking=True)
+        t.cuda.current_stream().synchronize()
+    return host.numpy()
+
+
+_NP2T = {}
 
 
 def _torch_dtype(dt):
     t = torch()
-    return {np.dtype(np.float64): t.float64, np.dtype(np.float32): t.float32,
-            np.dtype(np.int64): t.int64, np.dtype(np.int32): t.int32, np.dtype(np.int8): t.int8,
-            np.dtype(np.uint8): t.uint8, np.dtype(np.uint16): t.uint16}[np.dtype(dt)]
+    if not _NP2T:
+        _NP2T.update({np.dtype(np.float64): t.float64, np.dtype(np.float32): t.float32,
+                      np.dtype(np.int64): t.int64, np.dtype(np.int32): t.int32, np.dtype(np.int8): t.int8,
+                      np.dtype(np.uint8): t.uint8, np.dtype(np.uint16): t.uint16})
+    return _NP2T[np.dtype(dt)]
 
 
 def _numpy_dtype(dt):

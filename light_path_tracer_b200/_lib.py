@@ -57,6 +57,11 @@ SYMBOLS = {
     "lp_remap": (ctypes.c_int, [_VP, _I32, _I32, _CAMP, _VP, _VP, _I32, _I32, _I32, _I32, _VP, _VP]),
     "lp_render_frame": (ctypes.c_int, [_VP, _I32, _I32, _CAMP, _I32, _I32, _D, _D, _D, _D, _D,
                                        _I32, _I32, _VP, _VP, _VP, _VP, _U32, _VP]),
+    "lp_render_frame_bands": (ctypes.c_int, [_VP, _I32, _I32, _CAMP, _I32, _I32, _I32, _I32, _D, _D, _D, _D, _D,
+                                             _I32, _I32, _VP, _VP, _VP, _VP, _U32, _VP]),
+    "lp_render_schedule": (ctypes.c_int, [_CAMP, _I32, _I32, _D, _D, _D, _VP]),
+    "lp_peer_signal": (ctypes.c_int, [_VP, _I32, ctypes.c_uint64, _VP]),
+    "lp_peer_wait": (ctypes.c_int, [_VP, _I32, ctypes.c_uint64, _U32, _VP, _VP]),
     "lp_shadow_classify": (ctypes.c_int, [_I32, _I32, _D, _D, _VP, _VP, _VP]),
     "lp_frame_stats_reset": (ctypes.c_int, [_VP, _VP]),
     "lp_frame_stats_reduce": (ctypes.c_int, [_VP, _VP, _VP, _VP, _I64, _VP, _VP]),

@@ -148,21 +148,53 @@ void remap(const Tensor &src, int64_t channels, const std::vector<double> &camv,
 void render_frame(const Tensor &src, int64_t channels, const std::vector<double> &camv, int64_t row0, int64_t rows,
                   double M, double R_S, double r_obs, double phi_max, double h_max, bool loop_around,
                   int64_t sampling, Tensor out, OptTensor fa32, OptTensor w16, OptTensor stats, int64_t flags,
-                  bool unit_u8)
+                  bool unit_u8, int64_t band_rows, int64_t band_stride)
 {
     lp_camera cam = make_cam(camv);
     const int64_t n = rows * (int64_t)cam.width;
     int code = dtype_code(src);
     if (unit_u8) { TORCH_CHECK(code == LP_DTYPE_U8, "unit_u8 needs a uint8 image"); code = LP_DTYPE_U8_UNIT; }
     TORCH_CHECK(out.scalar_type() == src.scalar_type(), "out dtype must equal source dtype");
+    // a frame-addressed tile of interleaved bands must reach its last frame row
+    int64_t out_rows = rows;
+    if ((flags & LP_RENDER_OUT_FRAME_ROWS) && band_rows > 0 && rows > 0)
+        out_rows = ((rows - 1) / band_rows) * band_stride + ((rows - 1) % band_rows) + 1;
     c10::cuda::CUDAGuard g(src.device());
-    check(lp_render_frame(ptr(src, src.scalar_type(), "src", (int64_t)cam.height * cam.width * channels), code,
-                          (int32_t)channels, &cam, (int32_t)row0, (int32_t)rows, M, R_S, r_obs, phi_max, h_max,
-                          loop_around ? 1 : 0, (int32_t)sampling, ptr(out, out.scalar_type(), "out", n * channels),
-                          (float *)optptr(fa32, c10::ScalarType::Float, "fa32", n),
-                          (uint16_t *)optptr(w16, c10::ScalarType::UInt16, "w16", n), stats_ptr(stats),
-                          (uint32_t)flags, stream_of(src)),
-          "lp_render_frame");
+    check(lp_render_frame_bands(ptr(src, src.scalar_type(), "src", (int64_t)cam.height * cam.width * channels), code,
+                                (int32_t)channels, &cam, (int32_t)row0, (int32_t)rows, (int32_t)band_rows,
+                                (int32_t)band_stride, M, R_S, r_obs, phi_max, h_max,
+                                loop_around ? 1 : 0, (int32_t)sampling,
+                                ptr(out, out.scalar_type(), "out", out_rows * (int64_t)cam.width * channels),
+                                (float *)optptr(fa32, c10::ScalarType::Float, "fa32", n),
+                                (uint16_t *)optptr(w16, c10::ScalarType::UInt16, "w16", n), stats_ptr(stats),
+                                (uint32_t)flags, stream_of(src)),
+          "lp_render_frame_bands");
+}
+
+bool render_schedule(const std::vector<double> &camv, int64_t row0, int64_t rows, double M, double R_S, double r_obs)
+{
+    lp_camera cam = make_cam(camv);
+    int32_t repack = 0;
+    check(lp_render_schedule(&cam, (int32_t)row0, (int32_t)rows, M, R_S, r_obs, &repack), "lp_render_schedule");
+    return repack != 0;
+}
+
+// flag_ptrs: raw device addresses (possibly peer-mapped) as integers; stream = current stream of `device_of`
+void peer_signal(const std::vector<int64_t> &flag_ptrs, int64_t value, const Tensor &device_of)
+{
+    std::vector<uint64_t *> p;
+    for (int64_t v : flag_ptrs) p.push_back((uint64_t *)(uintptr_t)v);
+    c10::cuda::CUDAGuard g(device_of.device());
+    check(lp_peer_signal(p.data(), (int32_t)p.size(), (uint64_t)value, stream_of(device_of)), "lp_peer_signal");
+}
+
+void peer_wait(const Tensor &flags, int64_t n_flags, int64_t value, int64_t timeout_ms, OptTensor timed_out)
+{
+    c10::cuda::CUDAGuard g(flags.device());
+    check(lp_peer_wait((const uint64_t *)ptr(flags, c10::ScalarType::Long, "flags", n_flags), (int32_t)n_flags,
+                       (uint64_t)value, (uint32_t)timeout_ms,
+                       (int32_t *)optptr(timed_out, c10::ScalarType::Int, "timed_out", 1), stream_of(flags)),
+          "lp_peer_wait");
 }
 
 void shadow_classify(int64_t width, int64_t height, double fov, double alpha_crit, Tensor image, OptTensor n_shadow)
@@ -339,7 +371,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.def("trace_frame", &trace_frame);
     m.def("build_alpha_lookup", &build_alpha_lookup);
     m.def("remap", &remap);
-    m.def("render_frame", &render_frame);
+    m.def("render_frame", &render_frame, py::arg("src"), py::arg("channels"), py::arg("cam"), py::arg("row0"),
+          py::arg("rows"), py::arg("M"), py::arg("R_S"), py::arg("r_obs"), py::arg("phi_max"), py::arg("h_max"),
+          py::arg("loop_around"), py::arg("sampling"), py::arg("out"), py::arg("fa32"), py::arg("w16"),
+          py::arg("stats"), py::arg("flags"), py::arg("unit_u8"), py::arg("band_rows") = 0,
+          py::arg("band_stride") = 0);
+    m.def("render_schedule", &render_schedule);
+    m.def("peer_signal", &peer_signal);
+    m.def("peer_wait", &peer_wait);
     m.def("shadow_classify", &shadow_classify);
     m.def("stats_reset", &stats_reset);
     m.def("stats_reduce", &stats_reduce);

@@ -6,30 +6,12 @@
 // the alpha loads and the fa / winding stores are fully coalesced.  The ray state
 // (u, w, step index) lives in registers in fp64; the per-configuration constants and the
 // strided phi table arrive through the kernel parameter (constant) bank.
-#include "lp_internal.cuh"
-#include "lp_remap.cuh"
+#include "lp_trace.cuh"
 
 #include <stdlib.h>
 
-#define LP_TRACE_BLOCK 256          /* launch bound (max threads per CTA) */
 #define LP_RENDER_DEFAULT_TRIP 4
 #define LP_TRACE_DEFAULT_BLOCK 64   /* rays per CTA; LP_TRACE_BLOCK=32|64|128|256 overrides (tuning) */
-
-enum { SRC_F64 = 0, SRC_F32 = 1, SRC_CAM = 2 };
-
-struct TraceArgs {
-    const void *alphas;     // SRC_F64: const double*, SRC_F32: const float*, SRC_CAM: unused
-    long long n;            // rays in this launch
-    void *out_fa;           // WIDE: double*, else float*
-    void *out_w;            // WIDE: int64_t*, else uint16_t*
-    float *out_alpha32;     // SRC_CAM only, optional
-    int8_t *out_status;     // optional
-    int32_t *out_steps;     // optional
-    lp_frame_stats *stats;  // optional
-    int32_t row0;           // SRC_CAM: first frame row of the tile
-    int32_t retrace_steps;  // FUSED kernels: a ray that ran more RK4 steps than this is traced
-                            // again with strict arithmetic (LP_TRACE_HYBRID); INT_MAX = never
-};
 
 // LP_TRACE_HYBRID threshold.  The FMA-contracted loop differs from the strict one by ~1e-16
 // per operation; the difference grows like e^phi while a ray lingers at the photon sphere.
@@ -42,7 +24,7 @@ struct TraceArgs {
 // threshold is the number of steps that sweeps the same angle)
 #define LP_HYBRID_RETRACE_PHI 12.0
 
-static int retrace_steps_for(uint32_t flags, double h_max)
+int lp_retrace_steps_for(uint32_t flags, double h_max)
 {
     if (!(flags & LP_TRACE_HYBRID)) return 0x7fffffff;
     if (!(h_max > 0.0)) return 0;                       // degenerate step: everything strict
@@ -148,7 +130,7 @@ extern "C" int lp_schw_trace_batch_f64(const double *alphas, int64_t n,
     if (rc != LP_OK) return rc;
     CamConsts cam = {};
     TraceArgs a = {};
-    a.retrace_steps = retrace_steps_for(flags, h_max);
+    a.retrace_steps = lp_retrace_steps_for(flags, h_max);
     a.alphas = alphas; a.n = n; a.out_fa = out_fa; a.out_w = out_w;
     a.out_status = out_status; a.out_steps = out_steps; a.stats = stats;
     return launch_trace<SRC_F64, true>(a, c, cam, flags, (cudaStream_t)stream);
@@ -168,7 +150,7 @@ extern "C" int lp_schw_trace_alpha32(const float *alpha32, int64_t n,
     if (rc != LP_OK) return rc;
     CamConsts cam = {};
     TraceArgs a = {};
-    a.retrace_steps = retrace_steps_for(flags, h_max);
+    a.retrace_steps = lp_retrace_steps_for(flags, h_max);
     a.alphas = alpha32; a.n = n; a.out_fa = out_fa32; a.out_w = out_w16;
     a.out_status = out_status; a.out_steps = out_steps; a.stats = stats;
     return launch_trace<SRC_F32, false>(a, c, cam, flags, (cudaStream_t)stream);
@@ -191,7 +173,7 @@ extern "C" int lp_schw_trace_frame(const lp_camera *h_cam, int32_t row0, int32_t
     rc = lp_make_binet_consts(M, R_S, r_obs, phi_max, h_max, &c);
     if (rc != LP_OK) return rc;
     TraceArgs a = {};
-    a.retrace_steps = retrace_steps_for(flags, h_max);
+    a.retrace_steps = lp_retrace_steps_for(flags, h_max);
     a.n = n; a.out_fa = out_fa32; a.out_w = out_w16; a.out_alpha32 = out_alpha32;
     a.out_status = out_status; a.out_steps = out_steps; a.stats = stats; a.row0 = row0;
     return launch_trace<SRC_CAM, false>(a, c, cam, flags, (cudaStream_t)stream);
@@ -209,18 +191,20 @@ lp_render_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts c, con
     const LoopRegs L = load_loop_regs(c);
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < a.n;
-    // float32 RGB into a 16-byte aligned tile: a full warp's 32 pixels (384 contiguous bytes)
-    // are staged in shared memory and leave as 24 16-byte stores instead of 96 4-byte ones —
-    // full sectors, which is what peer (NVLink) destinations need (dist.PeerFrame).
+    // RGB (float32 or 8-bit) into a 16-byte aligned tile: a full warp's 32 pixels (384 / 96
+    // contiguous bytes) are staged in shared memory and leave as 24 / 6 16-byte stores instead
+    // of 96 4-byte / 1-byte ones — full sectors, which is what peer (NVLink) destinations need
+    // (dist.PeerFrame).
     __shared__ __align__(16) float stage[LP_TRACE_BLOCK / 32][96];
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     const long long i0 = i - lane;
-    const bool vec = sizeof(T) == 4 && ra.vec_ok && (i0 + 31 < a.n);      // warp-uniform
+    const bool vec = (sizeof(T) == 4 || sizeof(T) == 1) && ra.vec_ok && (i0 + 31 < a.n);      // warp-uniform
     RayResult r;
     r.status = 0; r.steps = 0; r.nh = 0; r.fa = 0.0;
+    long long oi = i;
     if (live) {
         int row, col;
-        pixel_row_col(i, a.n, cam.width, a.row0, row, col);
+        tile_pixel(a, cam.width, i, row, col, oi);
         const float a32 = (float)pixel_alpha64(cam, cam_x(cam, col), cam_y(cam, row));
         binet_trace<FUSED, FAST, TRIP>(c, L, (double)a32, r);
         if (FUSED && r.steps > a.retrace_steps) binet_trace<false, FAST>(c, L, (double)a32, r);
@@ -228,13 +212,16 @@ lp_render_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts c, con
         const long long nh = r.nh < 0 ? 0 : (r.nh > 65535 ? 65535 : r.nh);
         if (a.out_fa) ((float *)a.out_fa)[i] = fa32;
         if (a.out_w) ((unsigned short *)a.out_w)[i] = (unsigned short)nh;
-        T *dst = vec ? (T *)&stage[wrp][lane * 3] : (T *)ra.out + i * ra.channels;
+        T *dst = vec ? (T *)&stage[wrp][0] + lane * 3 : (T *)ra.out + oi * ra.channels;
         remap_pixel<T>(ra, cam, dst, row, col, fa32, (unsigned)nh);
     }
     if (vec) {
+        // vec_ok: the warp's 32 pixels are contiguous in the output (compact tile, or a frame-
+        // addressed tile whose width is a multiple of 32) and start on a 16-byte boundary
         __syncwarp();
-        if (lane < 24)
-            reinterpret_cast<float4 *>((float *)ra.out + i0 * 3)[lane] = reinterpret_cast<const float4 *>(stage[wrp])[lane];
+        const long long o0 = __shfl_sync(0xffffffffu, oi, 0);
+        if (lane < (int)(6 * sizeof(T)))
+            reinterpret_cast<uint4 *>((T *)ra.out + o0 * 3)[lane] = reinterpret_cast<const uint4 *>(stage[wrp])[lane];
     }
     if (a.stats) {
         StatAcc acc;
@@ -244,7 +231,7 @@ lp_render_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts c, con
     }
 }
 
-// RK4 steps per loop trip of the FMA fast path: LP_RENDER_TRIP=2|4 (tuning knob).
+// RK4 steps per loop trip of the fast path: LP_RENDER_TRIP=2|4 (tuning knob).
 static int render_trip()
 {
     static int cached = 0;
@@ -270,7 +257,8 @@ static int launch_render_mb(const TraceArgs &a, const RemapArgs &ra, const Binet
         else if (icmp) lp_render_kernel<true, true, T, MINB, 2><<<grid, block, 0, stream>>>(a, ra, c, cam);
         else      lp_render_kernel<true, false, T, MINB, 2><<<grid, block, 0, stream>>>(a, ra, c, cam);
     } else {
-        if (icmp) lp_render_kernel<false, true, T, MINB, 2><<<grid, block, 0, stream>>>(a, ra, c, cam);
+        if (icmp && render_trip() == 4) lp_render_kernel<false, true, T, MINB, 4><<<grid, block, 0, stream>>>(a, ra, c, cam);
+        else if (icmp) lp_render_kernel<false, true, T, MINB, 2><<<grid, block, 0, stream>>>(a, ra, c, cam);
         else      lp_render_kernel<false, false, T, MINB, 2><<<grid, block, 0, stream>>>(a, ra, c, cam);
     }
     return lp_check_launch();
@@ -285,17 +273,101 @@ static int launch_render(const TraceArgs &a, const RemapArgs &ra, const BinetCon
     return launch_render_mb<T, 4>(a, ra, c, cam, flags, stream);
 }
 
-extern "C" int lp_render_frame(const void *src, int32_t src_dtype, int32_t channels,
-                               const lp_camera *h_cam, int32_t row0, int32_t rows,
-                               double M, double R_S, double r_obs, double phi_max, double h_max,
-                               int32_t render_loop_around, int32_t sampling,
-                               void *out, float *out_fa32, uint16_t *out_w16,
-                               lp_frame_stats *stats, uint32_t flags, void *stream)
+// Frame rows of a (possibly interleaved) tile: last frame row + 1, or -1 for a bad request.
+static long long tile_row_end(int32_t row0, int32_t rows, int32_t band_rows, int32_t band_stride)
+{
+    if (row0 < 0 || rows < 0 || band_rows < 0) return -1;
+    if (band_rows == 0 || rows == 0) return (long long)row0 + rows;
+    if (band_stride < band_rows) return -1;
+    const long long r = rows - 1;
+    return (long long)row0 + (r / band_rows) * band_stride + (r % band_rows) + 1;
+}
+
+// ---------------------------------------------------------------------------
+// Schedule selection (one ray per thread vs lane re-packing, lp_repack.cu).
+//
+// Lanes idle in the one-ray-per-thread kernel when the 32 consecutive pixels of a warp need
+// very different numbers of RK4 steps.  That only happens in the annulus around the shadow
+// edge (viewing angle within ~[0.85, 1.45] of alpha_crit: captured rays stop early, rays that
+// graze the photon sphere orbit for a long time) and only if that annulus is NARROW in pixels,
+// so that one warp sees the whole variation.  Estimate of the lost lane fraction:
+//     (tile pixels inside the annulus / tile pixels) * min(1, 32 / annulus width in px)
+// computed exactly over the tile's rows from the projected circle (the BH direction's pinhole
+// projection, radius tan(alpha) * f).  Calibrated on B200 (tools/repack_perf.py).
+// ---------------------------------------------------------------------------
+#define LP_REPACK_LOSS_THRESHOLD 0.05
+
+static double annulus_px_in_rows(const CamConsts &cam, int32_t row0, int32_t rows, int32_t band_rows,
+                                 int32_t band_stride, double cx, double cy, double r_in, double r_out)
+{
+    double area = 0.0;
+    for (int r = 0; r < rows; ++r) {
+        const int row = row0 + (band_rows > 0 ? (r / band_rows) * band_stride + (r % band_rows) : r);
+        const double dy = (double)row + 0.5 - cy;
+        double len = 0.0;
+        const double ho2 = r_out * r_out - dy * dy;
+        if (ho2 > 0.0) {
+            const double ho = sqrt(ho2);
+            const double hi2 = r_in * r_in - dy * dy;
+            const double hi = hi2 > 0.0 ? sqrt(hi2) : 0.0;
+            // two chords [cx-ho, cx-hi] and [cx+hi, cx+ho], clipped to the frame's columns
+            const double segs[2][2] = {{cx - ho, cx - hi}, {cx + hi, cx + ho}};
+            for (int s = 0; s < 2; ++s) {
+                const double lo = segs[s][0] < 0.0 ? 0.0 : segs[s][0];
+                const double hi_c = segs[s][1] > (double)cam.width ? (double)cam.width : segs[s][1];
+                if (hi_c > lo) len += hi_c - lo;
+            }
+        }
+        area += len;
+    }
+    return area;
+}
+
+static int schedule_wants_repack(const CamConsts &cam, int32_t row0, int32_t rows, int32_t band_rows,
+                                 int32_t band_stride, double M, double R_S, double r_obs)
+{
+    if (rows <= 0 || cam.width <= 0) return 0;
+    if (!(cam.d2 > 1e-6) || !(r_obs > 1.5 * R_S)) return 0;      // BH behind / observer inside the photon sphere
+    const double f0 = 1.0 - R_S / r_obs;
+    const double s = 3.0 * sqrt(3.0) * M * sqrt(f0) / r_obs;    // sin(alpha_crit), metrics.py:753-755
+    if (!(s > 0.0) || !(s < 0.95)) return 0;
+    const double ac = asin(s);
+    const double a_in = 0.85 * ac, a_out = 1.45 * ac;
+    if (a_out > 1.2) return 0;
+    const double f = 0.5 * (cam.fx + cam.fy);
+    const double cx = cam.half_w + cam.fx * cam.d0 / cam.d2, cy = cam.half_h + cam.fy * cam.d1 / cam.d2;
+    const double r_in = tan(a_in) * f, r_out = tan(a_out) * f;
+    const double width_px = r_out - r_in;
+    const double area = annulus_px_in_rows(cam, row0, rows, band_rows, band_stride, cx, cy, r_in, r_out);
+    const double frac = area / ((double)rows * cam.width);
+    const double narrow = width_px < 32.0 ? 1.0 : 32.0 / width_px;
+    return frac * narrow > LP_REPACK_LOSS_THRESHOLD ? 1 : 0;
+}
+
+extern "C" int lp_render_schedule(const lp_camera *h_cam, int32_t row0, int32_t rows,
+                                  double M, double R_S, double r_obs, int32_t *repack)
 {
     CamConsts cam;
     int rc = lp_make_cam_consts(h_cam, &cam);
     if (rc != LP_OK) return rc;
-    if (row0 < 0 || rows < 0 || (long long)row0 + rows > cam.height) return LP_ERR_INVALID_ARG;
+    if (!repack || row0 < 0 || rows < 0 || (long long)row0 + rows > cam.height) return LP_ERR_INVALID_ARG;
+    *repack = schedule_wants_repack(cam, row0, rows, 0, 0, M, R_S, r_obs);
+    return LP_OK;
+}
+
+extern "C" int lp_render_frame_bands(const void *src, int32_t src_dtype, int32_t channels,
+                                     const lp_camera *h_cam, int32_t row0, int32_t rows,
+                                     int32_t band_rows, int32_t band_stride,
+                                     double M, double R_S, double r_obs, double phi_max, double h_max,
+                                     int32_t render_loop_around, int32_t sampling,
+                                     void *out, float *out_fa32, uint16_t *out_w16,
+                                     lp_frame_stats *stats, uint32_t flags, void *stream)
+{
+    CamConsts cam;
+    int rc = lp_make_cam_consts(h_cam, &cam);
+    if (rc != LP_OK) return rc;
+    const long long row_end = tile_row_end(row0, rows, band_rows, band_stride);
+    if (row_end < 0 || row_end > cam.height) return LP_ERR_INVALID_ARG;
     if (channels < 1 || channels > 4) return LP_ERR_INVALID_ARG;
     if (sampling != LP_SAMPLE_NEAREST && sampling != LP_SAMPLE_BILINEAR) return LP_ERR_INVALID_ARG;
     const long long n = (long long)rows * cam.width;
@@ -304,23 +376,48 @@ extern "C" int lp_render_frame(const void *src, int32_t src_dtype, int32_t chann
     BinetConsts c;
     rc = lp_make_binet_consts(M, R_S, r_obs, phi_max, h_max, &c);
     if (rc != LP_OK) return rc;
+    const bool frame_rows = (flags & LP_RENDER_OUT_FRAME_ROWS) != 0;
     TraceArgs a = {};
-    a.retrace_steps = retrace_steps_for(flags, h_max);
+    a.retrace_steps = lp_retrace_steps_for(flags, h_max);
     a.n = n; a.out_fa = out_fa32; a.out_w = out_w16; a.stats = stats; a.row0 = row0;
+    a.band_rows = band_rows; a.band_stride = band_stride;
+    a.out_frame_rows = (frame_rows && band_rows > 0) ? 1 : 0;     // contiguous rows: frame-addressed == compact
     RemapArgs ra;
     ra.src = src; ra.out = out; ra.fa32 = nullptr; ra.w16 = nullptr; ra.n = n;
     ra.row0 = row0; ra.channels = channels; ra.loop_around = render_loop_around; ra.sampling = sampling;
-    ra.vec_ok = ((flags & LP_RENDER_STAGED_STORES) && src_dtype == LP_DTYPE_F32 && channels == 3 &&
+    const bool contiguous32 = !a.out_frame_rows || cam.width % 32 == 0;
+    ra.vec_ok = ((flags & LP_RENDER_STAGED_STORES) && channels == 3 && contiguous32 &&
+                 (src_dtype == LP_DTYPE_F32 || src_dtype == LP_DTYPE_U8 || src_dtype == LP_DTYPE_U8_UNIT) &&
                  ((uintptr_t)out % 16) == 0) ? 1 : 0;
     ra.u8_scale = (src_dtype == LP_DTYPE_U8_UNIT) ? 255.0f : 1.0f;
     if (src_dtype == LP_DTYPE_U8_UNIT) src_dtype = LP_DTYPE_U8;
     cudaStream_t st = (cudaStream_t)stream;
+    // schedule: forced by flag, else predicted from the geometry; the re-packing kernel needs the
+    // fast-path precondition (observer strictly inside the integration band)
+    int repack = 0;
+    if (flags & LP_TRACE_REPACK) repack = 1;
+    else if (!(flags & LP_TRACE_NO_REPACK)) repack = schedule_wants_repack(cam, row0, rows, band_rows, band_stride, M, R_S, r_obs);
+    if (repack && lp_binet_fast_ok(&c) && c.valid && n <= 0x7fffffffLL) {
+        ra.vec_ok = (contiguous32 && ((uintptr_t)out % 16) == 0) ? 1 : 0;   // chunks are staged by construction
+        return lp_launch_render_repack(a, ra, c, cam, src_dtype, flags, st);
+    }
     switch (src_dtype) {
     case LP_DTYPE_U8: return launch_render<unsigned char>(a, ra, c, cam, flags, st);
     case LP_DTYPE_F32: return launch_render<float>(a, ra, c, cam, flags, st);
     case LP_DTYPE_F64: return launch_render<double>(a, ra, c, cam, flags, st);
     default: return LP_ERR_INVALID_ARG;
     }
+}
+
+extern "C" int lp_render_frame(const void *src, int32_t src_dtype, int32_t channels,
+                               const lp_camera *h_cam, int32_t row0, int32_t rows,
+                               double M, double R_S, double r_obs, double phi_max, double h_max,
+                               int32_t render_loop_around, int32_t sampling,
+                               void *out, float *out_fa32, uint16_t *out_w16,
+                               lp_frame_stats *stats, uint32_t flags, void *stream)
+{
+    return lp_render_frame_bands(src, src_dtype, channels, h_cam, row0, rows, 0, 0, M, R_S, r_obs, phi_max, h_max,
+                                 render_loop_around, sampling, out, out_fa32, out_w16, stats, flags, stream);
 }
 
 // ---------------------------------------------------------------------------

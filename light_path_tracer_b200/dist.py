@@ -124,53 +124,169 @@ class BandGather:
         return self.frame.reshape((self.world * self.rows,) + tuple(self.frame.shape[2:]))
 
 
+def band_layout(height, world_size, target_rows=27):
+    """Interleaved row bands for `world_size` ranks: the largest band height b <= target_rows with
+    height % (b * world_size) == 0, so that rank g owns bands g, g + G, g + 2G, ... (b rows each,
+    height / G rows in total).  Returns b, or None when the rows do not divide evenly (callers
+    then use contiguous row_tiles).  The black hole sits in the centre rows of a frame, so
+    contiguous tiles are unevenly expensive (config 4 at 8 GPUs: the slowest tile took 9 % longer
+    than the mean); a few dozen bands per rank average that out."""
+    if world_size < 1 or height <= 0 or height % world_size:
+        return None
+    per = height // world_size
+    for b in range(min(int(target_rows), per), 0, -1):
+        if per % b == 0:
+            return b
+    return None
+
+
+def band_rows_of(height, rank, world_size, band_rows):
+    """(row0, n_rows, (band_rows, band_stride)) of `rank` in the interleaved layout, and the frame
+    rows it owns as a numpy index array (for host-side assembly and tests)."""
+    per = height // world_size
+    stride = band_rows * world_size
+    r = np.arange(per)
+    frame_rows = rank * band_rows + (r // band_rows) * stride + (r % band_rows)
+    return rank * band_rows, per, (band_rows, stride), frame_rows
+
+
 class PeerFrame:
-    """The frame lives in rank `dst`'s HBM and every rank's render kernel stores its row tile
-    STRAIGHT INTO IT through NVLink peer memory (torch symmetric memory: CUDA VMM allocations
-    mapped into every process of the group).  The "gather" is the kernel's own pixel stores —
-    16-byte vectors, see lp_render_kernel — so the transfer overlaps the FP64 work store by
-    store and there is no copy kernel and no data-path collective; one tiny all-reduce orders
-    "every rank's kernel has finished" before rank `dst` reads the frame.
+    """The frame lives in rank `dst`'s HBM and every rank's render kernel stores its rows STRAIGHT
+    INTO IT through NVLink peer memory (torch symmetric memory: CUDA VMM allocations mapped into
+    every process of the group).  The "gather" is the kernel's own pixel stores — 16-byte vectors,
+    see lp_render_kernel / lp_render_repack_kernel — so the transfer overlaps the FP64 work store
+    by store; there is no copy kernel and NO collective on the data path or for completion: a
+    one-thread kernel per rank raises an 8-byte epoch flag in rank dst's memory (lp_peer_signal)
+    and rank dst's stream waits for all of them (lp_peer_wait).
 
-        pf = PeerFrame(H, (W, 3), torch.float32, device)       # collective (rendezvous)
-        render(rows=pf.rows, out=pf.tile)                      # every rank, its own tile
-        frame = pf.complete()                                  # [H, W, 3] on dst, None elsewhere
+        pf = PeerFrame(H, (W, 3), torch.uint8, device)          # collective (rendezvous), once
+        for every frame:
+            tile, rows, bands, fl = pf.begin()                  # every rank
+            render(rows=rows, bands=bands, flags=flags | fl, out=tile)
+            frame = pf.complete()                               # [H, W, 3] on dst, None elsewhere
 
-    Raises if symmetric memory is unavailable (callers fall back to BandGather / gather_rows)."""
+    Ownership: the tensor `complete()` returns on dst is one of ``buffers`` (2) symmetric frame
+    buffers and stays valid UNTIL THE NEXT complete() on dst; work that consumes it must be
+    enqueued (same stream) before that call.  Peers never overwrite a buffer the root may still be
+    reading: frame e goes to buffer e % buffers, and begin() makes the render wait (on the device)
+    until the root has released frame e - buffers, which the root does — stream-ordered after its
+    consumers — at the start of complete().  A peer can therefore run at most one frame ahead.
+    Device-side waits give up after ``timeout_ms`` (a dead peer cannot hang the GPU); `timed_out()`
+    reports it.
 
-    def __init__(self, height, row_shape, dtype, device, dst=0, group=None):
+    ``band_rows``: interleave the ranks' rows in bands of that many rows (band_layout) instead of
+    contiguous tiles.  Raises if symmetric memory is unavailable (callers fall back to BandGather /
+    gather_rows); the availability check is agreed on with a collective BEFORE the rendezvous, so a
+    one-sided failure cannot leave the other ranks waiting in it."""
+
+    _DONE, _CONSUMED, _TIMEOUT = 0, 32, 40        # int64 slots of the flag pad
+
+    def __init__(self, height, row_shape, dtype, device, dst=0, group=None, buffers=2, band_rows=None,
+                 timeout_ms=10000):
         import torch
         import torch.distributed as dist
-        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
         self.dist, self.dst = dist, dst
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
-        shape = (height,) + tuple(row_shape)
-        self.buf = symm_mem.empty(shape, dtype=dtype, device=device)
+        if self.world > 16:
+            raise ValueError("PeerFrame serves one NVLink domain (<= 16 ranks)")
+        self._ext = _lib.ext()
+        self.height, self.row_shape = int(height), tuple(row_shape)
+        self.buffers = max(1, int(buffers))
+        self.timeout_ms = int(timeout_ms)
+        shape = (self.buffers, self.height) + self.row_shape
+        ok, err = 1.0, None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            self.buf = symm_mem.empty(shape, dtype=dtype, device=device)
+            self.pad = symm_mem.empty(64, dtype=torch.int64, device=device)
+        except Exception as exc:                       # local allocation failed: tell everybody
+            ok, err = 0.0, exc
+        agree = torch.tensor([ok], device=device)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN, group=self.group)
+        if float(agree[0]) != 1.0:
+            raise RuntimeError("symmetric memory unavailable on at least one rank (%r)" % (err,))
         self.handle = symm_mem.rendezvous(self.buf, self.group)
-        self.root = self.handle.get_buffer(dst, shape, dtype)
-        self.rows = row_tiles(height, self.world)[self.rank]
-        self.tile = self.root[self.rows[0]:self.rows[0] + self.rows[1]]
-        self._flag = torch.zeros(1, dtype=torch.float32, device=device)
+        self.pad_handle = symm_mem.rendezvous(self.pad, self.group)
+        self.pad.zero_()
+        torch.cuda.synchronize(device)
+        dist.barrier(group=self.group)                 # every pad is zero before anybody signals
+        frame_numel = self.height * int(np.prod(self.row_shape))
+        self.root = [self.handle.get_buffer(dst, (self.height,) + self.row_shape, dtype, b * frame_numel)
+                     for b in range(self.buffers)]
+        self.local = [self.buf[b] for b in range(self.buffers)]
+        self._pad_ptrs = [int(p) for p in self.pad_handle.buffer_ptrs]
+        if band_rows:
+            if self.height % (int(band_rows) * self.world):
+                raise ValueError("band_rows * world_size must divide the frame height")
+            row0, rows, bands, _ = band_rows_of(self.height, self.rank, self.world, int(band_rows))
+            self.rows, self.bands = (row0, rows), bands
+        else:
+            self.rows, self.bands = row_tiles(self.height, self.world)[self.rank], None
+        self.epoch = 0
+
+    def begin(self):
+        """Start frame epoch+1: returns (tile tensor in rank dst's buffer, (row0, n_rows), bands,
+        extra render flags).  Makes the current stream wait until the buffer is free."""
+        from . import _device as dev
+        self.epoch += 1
+        e = self.epoch
+        if e > self.buffers:
+            self._ext.peer_wait(self.pad[self._CONSUMED:self._CONSUMED + 1], 1, e - self.buffers, self.timeout_ms,
+                                self.pad[self._TIMEOUT:self._TIMEOUT + 1].view(self._i32()))
+        root = self.root[e % self.buffers]
+        row0, rows = self.rows
+        if self.bands is None:
+            return root[row0:row0 + rows], self.rows, None, dev.RENDER_STAGED_STORES
+        return root[row0:], self.rows, self.bands, dev.RENDER_STAGED_STORES | dev.RENDER_OUT_FRAME_ROWS
 
     def complete(self):
-        # stream-ordered after this rank's render kernel; finishes on dst only after every
-        # rank's kernel (and therefore its peer stores) has finished
-        self.dist.all_reduce(self._flag, group=self.group)
-        return self.buf if self.rank == self.dst else None
+        """Stream-ordered after this rank's render kernel: raise this rank's flag on dst; on dst,
+        release the previous frame to the peers and wait for every rank's flag."""
+        e = self.epoch
+        self._ext.peer_signal([self._pad_ptrs[self.dst] + 8 * (self._DONE + self.rank)], e, self.pad)
+        if self.rank != self.dst:
+            return None
+        if e >= 2:
+            self._ext.peer_signal([p + 8 * self._CONSUMED for p in self._pad_ptrs], e - 1, self.pad)
+        self._ext.peer_wait(self.pad[self._DONE:self._DONE + self.world], self.world, e, self.timeout_ms,
+                            self.pad[self._TIMEOUT:self._TIMEOUT + 1].view(self._i32()))
+        return self.local[e % self.buffers]
+
+    def drain(self):
+        """dst: release every frame handed out so far (call when done, before the buffers are
+        reused by a new sequence or freed); then a barrier so that nobody tears the pads down early."""
+        if self.rank == self.dst and self.epoch >= 1:
+            self._ext.peer_signal([p + 8 * self._CONSUMED for p in self._pad_ptrs], self.epoch, self.pad)
+        self.dist.barrier(group=self.group)
+
+    def timed_out(self):
+        """True if a device-side wait of this rank gave up (synchronises)."""
+        return bool(int(self.pad[self._TIMEOUT].item()) != 0)
+
+    def _i32(self):
+        import torch
+        return torch.int32
 
 
 class ShardedHostFrames:
-    """Host image in -> this rank's row tile of the lensed frame out, for streams of frames, with
-    the upload SHARDED: every rank copies only its own 1/N of the rows of the source image over
-    its own PCIe link, one NCCL all-gather over NVLink assembles the replicated source on every
-    GPU (the remap may sample any source pixel), the fused kernel renders the rank's tile, the
-    tile goes back to (pinned) host memory.  PCIe carries 1/N of the source per GPU instead of
-    all of it; ``depth`` slots on their own streams overlap one frame's upload with the previous
-    frame's download, as image_lens.HostFramePipeline does on one GPU.  Needs equal row tiles."""
+    """Host image in -> this rank's rows of the lensed frame out, for streams of frames, with the
+    upload SHARDED and the source RESIDENT: every rank copies only its own 1/N of the rows of a
+    NEW source image over its own PCIe link and one NCCL all-gather over NVLink assembles the
+    replicated source on every GPU (the remap may sample any source pixel); a source that has not
+    changed (same ``version``) is not uploaded or gathered again — sweeps over one background move
+    only camera parameters in and tiles out.  The fused kernel renders the rank's rows; the tile
+    goes back to (pinned) host memory.  ``depth`` slots on their own streams overlap one frame's
+    upload with the previous frame's download, as image_lens.HostFramePipeline does on one GPU; two
+    resident source buffers let the next image arrive while the current one is still being sampled.
+    Needs equal row tiles.  ``unit_u8``: uint8 images standing for float32/255 — the 8-bit
+    boundary of image_lens.main (image_lens.py:448-450, :510), 4x fewer bytes on PCIe than
+    float32 frames."""
 
-    def __init__(self, shape, dtype, vertical_fov=None, metric=None, depth=3, group=None):
+    def __init__(self, shape, dtype, vertical_fov=None, metric=None, depth=3, group=None, unit_u8=False,
+                 band_rows=None):
         import torch
         import torch.distributed as dist
         from .metrics import Schwarzschild
@@ -182,22 +298,36 @@ class ShardedHostFrames:
         tiles = row_tiles(self.height, self.world)
         if any(r != tiles[0][1] for _, r in tiles):
             raise ValueError("ShardedHostFrames needs equal row tiles")
-        self.rows = tiles[self.rank]
+        self.part_rows = tiles[self.rank]              # the rows of the SOURCE this rank uploads
+        if band_rows:
+            row0, rows, bands, self.frame_rows = band_rows_of(self.height, self.rank, self.world, int(band_rows))
+            self.rows, self.bands = (row0, rows), bands
+        else:
+            self.rows, self.bands = tiles[self.rank], None
+            self.frame_rows = np.arange(self.rows[0], self.rows[0] + self.rows[1])
         self.metric = metric if metric is not None else Schwarzschild(M=1.0)
         self.fov = vertical_fov
+        self.unit_u8 = bool(unit_u8)
         device = torch.device("cuda", torch.cuda.current_device())
         tile_shape = (self.rows[1],) + self.shape[1:]
-        self._slots = [dict(stream=torch.cuda.Stream(device=device),
-                            part=torch.empty(tile_shape, dtype=dtype, device=device),
-                            src=torch.empty(self.shape, dtype=dtype, device=device),
-                            frame=torch.empty(tile_shape, dtype=dtype, device=device))
-                       for _ in range(max(1, int(depth)))]
+        self._slots = []
+        for _ in range(max(1, int(depth))):
+            st = torch.cuda.Stream(device=device)
+            with torch.cuda.stream(st):
+                self._slots.append(dict(stream=st, part=torch.empty(tile_shape, dtype=dtype, device=device),
+                                        frame=torch.empty(tile_shape, dtype=dtype, device=device), done=None))
+        # two resident, replicated sources: {buf, version, ready event, last-use events}
+        self._res = [dict(buf=torch.empty(self.shape, dtype=dtype, device=device), version=None, ready=None, uses=[])
+                     for _ in range(2)]
+        self._cur = 0
         self._k = 0
+        self.uploads = 0
         self._torch = torch
 
-    def submit(self, host_src, fov, r_obs, psi=(0.0, 0.0), out=None, flags=None):
-        """host_src: the full [H, W, ...] pinned host image (only this rank's rows are read).
-        Returns the pinned host tensor that holds this rank's tile after synchronize()."""
+    def submit(self, host_src, fov, r_obs, psi=(0.0, 0.0), out=None, flags=None, version=None):
+        """host_src: the full [H, W, ...] pinned host image (only this rank's rows are read, and
+        only when ``version`` differs from the resident one; ``version=None`` = a new image every
+        call).  Returns the pinned host tensor that holds this rank's tile after synchronize()."""
         from . import image_lens as il
         from . import _device as dev
         t = self._torch
@@ -205,15 +335,33 @@ class ShardedHostFrames:
         self._k += 1
         row0, n = self.rows
         if out is None:
-            out = t.empty((n,) + self.shape[1:], dtype=slot["src"].dtype).pin_memory()
+            out = t.empty((n,) + self.shape[1:], dtype=slot["frame"].dtype).pin_memory()
         st = slot["stream"]
         st.wait_stream(t.cuda.current_stream())
         with t.cuda.stream(st):
-            slot["part"].copy_(host_src[row0:row0 + n], non_blocking=True)
-            self.dist.all_gather_into_tensor(slot["src"].view(self.world, -1), slot["part"].view(-1),
-                                             group=self.group)
-            il.render_frame(slot["src"], fov, r_obs, self.metric, psi=psi, rows=(row0, n),
-                            flags=dev.TRACE_HYBRID if flags is None else flags, out=slot["frame"])
+            res = self._res[self._cur]
+            if version is None or res["version"] != version:
+                res = self._res[1 - self._cur]
+                for ev in res["uses"]:                 # frames still sampling the buffer we are about to overwrite
+                    st.wait_event(ev)
+                res["uses"] = []
+                p0, pn = self.part_rows
+                slot["part"].copy_(host_src[p0:p0 + pn], non_blocking=True)
+                self.dist.all_gather_into_tensor(res["buf"].view(self.world, -1), slot["part"].view(-1),
+                                                 group=self.group)
+                res["version"] = version
+                res["ready"] = t.cuda.Event()
+                res["ready"].record(st)
+                self._cur = 1 - self._cur
+                self.uploads += 1
+            else:
+                st.wait_event(res["ready"])
+            il.render_frame(res["buf"], fov, r_obs, self.metric, psi=psi, rows=(row0, n), bands=self.bands,
+                            flags=dev.TRACE_HYBRID if flags is None else flags, out=slot["frame"],
+                            unit_u8=self.unit_u8)
+            used = t.cuda.Event()
+            used.record(st)
+            res["uses"] = res["uses"][-(len(self._slots) - 1):] + [used]
             out.copy_(slot["frame"], non_blocking=True)
         return out
 
@@ -279,19 +427,15 @@ class RowShardedRenderer:
             equal = all(r == self.tiles[0][1] for _, r in self.tiles)
             self._root_dst, self._root_frame, self._root_gather = dst, None, None
             ok = 0.0
+            # every rank takes the same branch here (`equal` is a function of the frame and the world
+            # size), and PeerFrame agrees on availability with a collective before its rendezvous
             if equal and self.pipe.src.is_cuda:
                 try:
                     self._root_frame = self._new_peer_frame(dst)
                     ok = 1.0
-                except Exception:                       # symmetric memory unavailable
+                except RuntimeError:                    # symmetric memory unavailable (agreed by all ranks)
                     self._root_frame = None
-            agree = torch.tensor([ok], device=self.pipe.src.device)
-            dist.all_reduce(agree, op=dist.ReduceOp.MIN, group=self.group)
-            if float(agree[0]) == 1.0:
-                mode = "peer"
-            else:
-                self._root_frame = None
-                mode = "bands" if equal else "tiles"
+            mode = "peer" if ok == 1.0 else ("bands" if equal else "tiles")
             self._root_mode = mode
         if mode == "peer":
             return self.render_peer(r_obs, psi, stats, flags, frame=self._root_frame, dst=dst)
@@ -306,17 +450,19 @@ class RowShardedRenderer:
 
     def _new_peer_frame(self, dst):
         return PeerFrame(self.pipe.height, (self.pipe.width,) + tuple(self.pipe.src.shape[2:]),
-                         self.pipe.src.dtype, self.pipe.src.device, dst=dst, group=self.group)
+                         self.pipe.src.dtype, self.pipe.src.device, dst=dst, group=self.group,
+                         band_rows=band_layout(self.pipe.height, self.world))
 
-    def render_peer(self, r_obs, psi=(0.0, 0.0), stats=None, flags=None, frame=None, dst=0):
-        """Render this rank's tile directly into rank dst's frame over NVLink (PeerFrame).  Pass a
-        PeerFrame to reuse its mapping across frames (creating one is a rendezvous)."""
+    def render_peer(self, r_obs, psi=(0.0, 0.0), stats=None, flags=None, frame=None, dst=0, unit_u8=False):
+        """Render this rank's rows directly into rank dst's frame over NVLink (PeerFrame).  Pass a
+        PeerFrame to reuse its mapping across frames (creating one is a rendezvous).  The returned
+        frame (dst only) is valid until the next call (PeerFrame's ownership rule)."""
         flags = self._default_flags() if flags is None else flags
         if frame is None:
             frame = self._new_peer_frame(dst)
-        from . import _device as dev
-        self.pipe.render(r_obs, psi=psi, rows=frame.rows, stats=stats, flags=flags | dev.RENDER_STAGED_STORES,
-                         out=frame.tile)
+        tile, rows, bands, extra = frame.begin()
+        self.pipe.render(r_obs, psi=psi, rows=rows, bands=bands, stats=stats, flags=flags | extra, out=tile,
+                         unit_u8=unit_u8)
         return frame.complete()
 
     @staticmethod

@@ -38,11 +38,25 @@ class OdeResult(dict):
             raise AttributeError(name) from e
 
 
+def _builtin_rhs(metric, base, need_initial_conditions):
+    """The kernel carries `base`'s own right-hand side (and initial conditions): a subclass that
+    overrides them would be silently ignored, so it is refused instead."""
+    cls = type(metric)
+    names = ["geodesic_equations"] + (["initial_conditions"] if need_initial_conditions else [])
+    changed = [n for n in names if getattr(cls, n) is not getattr(base, n)]
+    if changed:
+        raise NotImplementedError(
+            "%s overrides %s: the CUDA generic integrator evaluates %s's own %s on the device and has "
+            "no host callback path (no CPU fallback)" % (cls.__name__, ", ".join(changed), base.__name__,
+                                                         " / ".join(names)))
+
+
 def _require_schwarzschild(metric):
     if not isinstance(metric, Schwarzschild):
         raise NotImplementedError(
             "this entry point evaluates Schwarzschild.initial_conditions on the device "
             "(metrics.py:794-809); %s is not supported" % type(metric).__name__)
+    _builtin_rhs(metric, Schwarzschild, True)
 
 
 def _require_known_metric(metric):
@@ -50,6 +64,7 @@ def _require_known_metric(metric):
         raise NotImplementedError(
             "the CUDA generic integrator carries the Schwarzschild and Kerr right-hand sides "
             "(metrics.py:763-790, :946-1029); %s is not supported" % type(metric).__name__)
+    _builtin_rhs(metric, Kerr if isinstance(metric, Kerr) else Schwarzschild, False)
 
 
 def _alloc(t, n, device):

@@ -153,13 +153,21 @@ def precompute_final_alpha_lookup(alpha_lookup, alpha_crit, r_obs, metric):
 
     if isinstance(metric, Schwarzschild) and type(metric).trace_rays_batch is Schwarzschild.trace_rays_batch:
         t = dev.torch()
-        if tensor_in:
-            a32 = alpha_lookup.contiguous()
-            if a32.dtype != t.float32:
-                a32 = a32.to(t.float32)
+        is_f32 = (alpha_lookup.dtype == t.float32) if tensor_in else (np.asarray(alpha_lookup).dtype == np.float32)
+        if is_f32:
+            a32 = alpha_lookup.contiguous() if tensor_in else dev.h2d(np.asarray(alpha_lookup), "alpha")
+            fa, w = metric.trace_alpha_table(a32, r_obs)
         else:
-            a32 = dev.h2d(np.asarray(alpha_lookup, dtype=np.float32), "alpha")
-        fa, w = metric.trace_alpha_table(a32, r_obs)
+            # the reference traces alpha_lookup.ravel().astype(float64) (image_lens.py:157): a table that
+            # is not float32 keeps its precision through the fp64 kernel and only the RESULTS are
+            # narrowed (image_lens.py:176-177)
+            a64 = (alpha_lookup.to(t.float64).contiguous() if tensor_in
+                   else dev.h2d(np.asarray(alpha_lookup, dtype=np.float64), "alpha"))
+            fa64 = t.empty(shape, dtype=t.float64, device=a64.device)
+            w64 = t.empty(shape, dtype=t.int64, device=a64.device)
+            metric.trace_rays_batch(r_obs, a64.view(-1), fa64.view(-1), w64.view(-1), flags=dev.TRACE_HYBRID)
+            fa = fa64.to(t.float32)
+            w = w64.clamp(0, WINDING_MAX).to(t.uint16)
         if tensor_in:
             return fa, w, n, n
         return dev.d2h(fa, "fa32"), dev.d2h(w, "w16"), n, n
@@ -189,6 +197,20 @@ def _axis_refine_columns(width, fx, psi):
     x_rel = x_cam - bh_x_cam
     x_abs_max = max(float(np.max(np.abs(x_rel))), 1e-12)
     return np.abs(x_rel) <= (Y_AXIS_REFINE_FRAC * x_abs_max)
+
+
+def _axis_refine_columns_device(width, fx, psi):
+    """_axis_refine_columns as a uint8 CUDA tensor, built on the device (no host staging, so it can
+    be captured in a CUDA graph): the same IEEE subtractions / divisions column by column; the
+    maximum of |x_rel| is attained at the first or the last column and is taken on the host."""
+    t = dev.torch()
+    _, bh_x_cam, in_front = _psi_to_cam_projection(psi)
+    if not in_front or width == 0:
+        return t.zeros(width, dtype=t.uint8, device=dev.device())
+    ends = (np.array([0.0, float(width - 1)]) - width / 2) / fx - bh_x_cam
+    x_abs_max = max(float(np.max(np.abs(ends))), 1e-12)
+    x_rel = (t.arange(width, dtype=t.float64, device=dev.device()) - width / 2) / fx - bh_x_cam
+    return (x_rel.abs() <= (Y_AXIS_REFINE_FRAC * x_abs_max)).to(t.uint8)
 
 
 def _theta_pixel(image_dimension, fov, psi, rows):
@@ -238,7 +260,7 @@ def precompute_final_alpha_lookup_2d(alpha_lookup, fov, alpha_crit, r_obs, metri
         w_out = t.zeros(shape, dtype=t.uint16, device=a32.device)
         if n_traced:
             cam = dev.camera_vector(shape, fov, psi, _psi_frame)
-            d_cols = dev.h2d(refine_cols.astype(np.uint8), "refine_cols")
+            d_cols = _axis_refine_columns_device(width, fx, psi)
             fa, w = metric.trace_alpha_table_2d(a32, cam, r_obs, theta_obs, row0=0, refine_cols=d_cols)
             fa_out[:trace_rows] = fa
             w_out[:trace_rows] = w
@@ -330,12 +352,18 @@ def render_lensed_image(source_image, alpha_lookup, final_alpha_lookup, winding_
 
 def render_frame(source_image, fov, r_obs, metric, psi=(0.0, 0.0), render_loop_around=False, *,
                  sampling=SAMPLE_NEAREST, rows=None, return_lookups=False, stats=None,
-                 flags=dev.TRACE_HYBRID, out=None, unit_u8=False, theta_obs=np.pi / 2):
+                 flags=dev.TRACE_HYBRID, out=None, unit_u8=False, theta_obs=np.pi / 2, bands=None):
     """Fully fused device-resident frame (lp_render_frame): build_alpha_lookup +
     precompute_final_alpha_lookup + render_lensed_image in ONE launch, bit-identical to
     running the three stages back to back.  ``source_image`` is a CUDA tensor [H,W(,C)];
     ``rows=(row0, n_rows)`` renders a row tile (multi-GPU sharding).  Returns the CUDA
     frame tensor (and the float32 / uint16 lookups with ``return_lookups``).
+
+    ``bands=(band_rows, band_stride)`` makes the tile an INTERLEAVED set of rows (tile-local row r
+    is frame row ``row0 + (r // band_rows) * band_stride + r % band_rows``; dist.band_layout):
+    the black hole sits in the centre rows, so contiguous tiles are unevenly expensive.  With
+    ``flags | RENDER_OUT_FRAME_ROWS`` ``out`` is the FULL-frame tensor from row ``row0`` on and
+    every pixel is stored at its frame row (peer frames); otherwise ``out`` is a compact tile.
 
     A ``Kerr`` metric takes the device-resident three-launch path (alpha lookup, Kerr tracer
     with the per-pixel screen angle, remap) for the observer inclination ``theta_obs``; every
@@ -346,9 +374,20 @@ def render_frame(source_image, fov, r_obs, metric, psi=(0.0, 0.0), render_loop_a
     row0, n_rows = (0, height) if rows is None else rows
     src = source_image.contiguous()
     tile_shape = (n_rows, width) + tuple(source_image.shape[2:])
+    band_rows, band_stride = (0, 0) if bands is None else (int(bands[0]), int(bands[1]))
     if out is None:
+        if flags & dev.RENDER_OUT_FRAME_ROWS:
+            raise ValueError("a frame-addressed tile needs the caller's frame tensor as `out`")
         out = t.empty(tile_shape, dtype=src.dtype, device=src.device)
+    for base in (Kerr, Schwarzschild):
+        if isinstance(metric, base) and type(metric).trace_rays_batch is not base.trace_rays_batch:
+            raise NotImplementedError("%s overrides trace_rays_batch: render_frame runs %s's own tracer on the "
+                                      "device; use the staged calls (precompute_final_alpha_lookup -> "
+                                      "render_lensed_image), which drive the metric's own method"
+                                      % (type(metric).__name__, base.__name__))
     if isinstance(metric, Kerr):
+        if band_rows:
+            raise NotImplementedError("interleaved row bands cover the Schwarzschild fused kernel")
         return _render_frame_kerr(src, channels, fov, r_obs, metric, psi, render_loop_around, sampling,
                                   (row0, n_rows), return_lookups, out, unit_u8, theta_obs)
     if not isinstance(metric, Schwarzschild):
@@ -360,7 +399,7 @@ def render_frame(source_image, fov, r_obs, metric, psi=(0.0, 0.0), render_loop_a
     cam = dev.camera_vector((height, width), fov, psi, _psi_frame)
     e.render_frame(src, channels, cam, int(row0), int(n_rows), float(metric.M), float(metric.R_S),
                    float(r_obs), dev.PHI_MAX, dev.H_MAX, bool(render_loop_around), int(sampling),
-                   out, fa, w, stats, int(flags), bool(unit_u8))
+                   out, fa, w, stats, int(flags), bool(unit_u8), band_rows, band_stride)
     if return_lookups:
         return out, fa, w
     return out
@@ -376,7 +415,7 @@ def _render_frame_kerr(src, channels, fov, r_obs, metric, psi, loop_around, samp
     a32 = t.empty((n_rows, width), dtype=t.float32, device=src.device)
     e.build_alpha_lookup(cam, int(row0), int(n_rows), -1, a32)
     fx, _ = _focal((height, width), fov)
-    d_cols = dev.h2d(_axis_refine_columns(width, fx, psi).astype(np.uint8), "refine_cols")
+    d_cols = _axis_refine_columns_device(width, fx, psi)
     fa, w = metric.trace_alpha_table_2d(a32, cam, r_obs, theta_obs, row0=row0, refine_cols=d_cols)
     e.remap(src, channels, cam, fa, w, bool(loop_around), int(sampling), int(row0), int(n_rows), out, bool(unit_u8))
     if return_lookups:
@@ -397,9 +436,10 @@ class LensPipeline:
         self.fov = (2 * np.arctan(np.tan(vfov / 2) * self.width / self.height), vfov)  # image_lens.py:461-463
         self._t = t
 
-    def render(self, r_obs, psi=(0.0, 0.0), rows=None, stats=None, flags=dev.TRACE_HYBRID, out=None):
+    def render(self, r_obs, psi=(0.0, 0.0), rows=None, stats=None, flags=dev.TRACE_HYBRID, out=None, bands=None,
+               unit_u8=False):
         return render_frame(self.src, self.fov, r_obs, self.metric, psi=psi, rows=rows, stats=stats,
-                            flags=flags, out=out)
+                            flags=flags, out=out, bands=bands, unit_u8=unit_u8)
 
     def capture_sweep(self, params, out, flags=dev.TRACE_HYBRID, lanes=2):
         """Capture a whole parameter sweep — ``params`` = [(r_obs, psi), ...], frame j written to
@@ -462,9 +502,12 @@ class HostFramePipeline:
         vfov = np.radians(vertical_fov_deg)
         self.fov = (2 * np.arctan(np.tan(vfov / 2) * self.width / self.height), vfov)
         device = dev.device()
-        self._slots = [dict(stream=t.cuda.Stream(device=device),
-                            src=t.empty(self.shape, dtype=dtype, device=device), frame=None)
-                       for _ in range(max(1, int(depth)))]
+        self._slots = []
+        for _ in range(max(1, int(depth))):
+            st = t.cuda.Stream(device=device)
+            with t.cuda.stream(st):         # the slot's buffers are allocated on (and only ever used on) its stream
+                src = t.empty(self.shape, dtype=dtype, device=device)
+            self._slots.append(dict(stream=st, src=src, frame=None))
         self._k = 0
         self._t = t
 
@@ -477,11 +520,13 @@ class HostFramePipeline:
         tile_shape = (n_rows,) + self.shape[1:]
         if out is None:
             out = t.empty(tile_shape, dtype=slot["src"].dtype).pin_memory()
-        if slot["frame"] is None or tuple(slot["frame"].shape) != tile_shape:
-            slot["frame"] = t.empty(tile_shape, dtype=slot["src"].dtype, device=slot["src"].device)
         st = slot["stream"]
         st.wait_stream(t.cuda.current_stream())
         with t.cuda.stream(st):
+            if slot["frame"] is None or tuple(slot["frame"].shape) != tile_shape:
+                # allocated on the slot's stream: the caching allocator then orders the reuse of the
+                # old block after the work that stream still has queued on it
+                slot["frame"] = t.empty(tile_shape, dtype=slot["src"].dtype, device=slot["src"].device)
             slot["src"].copy_(host_src, non_blocking=True)
             render_frame(slot["src"], self.fov if fov is None else fov, r_obs, self.metric, psi=psi, rows=rows,
                          flags=flags, out=slot["frame"], unit_u8=self.unit_u8)

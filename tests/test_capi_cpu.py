@@ -36,7 +36,7 @@ def test_sm100a_code_present(native):
 
 def test_abi_basics(native):
     lib = native.capi()
-    assert lib.lp_abi_version() == 1
+    assert lib.lp_abi_version() == 2
     assert lib.lp_error_string(0) == b"ok"
     assert b"invalid" in lib.lp_error_string(-1)
     assert lib.lp_device_count() >= 0

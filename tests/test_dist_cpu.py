@@ -26,6 +26,20 @@ def test_row_tiles_partition():
             b = band_splits(rows, bands)
             assert sum(n for _, n in b) == rows and all(n > 0 for _, n in b)
             assert all(b[k][0] + b[k][1] == b[k + 1][0] for k in range(len(b) - 1))
+    from light_path_tracer_b200.dist import band_layout, band_rows_of
+    for H, G in ((4320, 8), (4320, 2), (2160 * 8, 8), (540, 2), (1080, 4), (96, 3)):
+        b = band_layout(H, G)
+        assert b is not None and 1 <= b <= 27 and H % (b * G) == 0
+        owned = []
+        for g in range(G):
+            row0, rows, (br, stride), frame_rows = band_rows_of(H, g, G, b)
+            assert row0 == g * b and rows == H // G and br == b and stride == b * G
+            # the kernel's mapping (lp_trace.cuh tile_pixel): r -> row0 + (r // b) * stride + r % b
+            r = np.arange(rows)
+            assert np.array_equal(frame_rows, row0 + (r // b) * stride + (r % b))
+            owned.append(frame_rows)
+        assert np.array_equal(np.sort(np.concatenate(owned)), np.arange(H))
+    assert band_layout(4321, 8) is None and band_layout(7, 2) is None and band_layout(8, 2, 3) == 2
     grid = sweep_grid()
     assert len(grid) == 512 and grid[0][0] == 15.0 and abs(grid[-1][0] - 1000.0) < 1e-9
 

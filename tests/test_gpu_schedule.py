@@ -1,0 +1,151 @@
+"""GPU parity of the schedules added for multi-GPU frames and divergent frames: interleaved row
+bands (lp_render_frame_bands), 16-byte staged stores for 8-bit tiles, the lane re-packing frame
+kernel (lp_render_repack_kernel, LP_TRACE_REPACK) and the peer completion flags.  Everything here
+must reproduce the one-launch, one-ray-per-thread frame BIT FOR BIT: the schedules only move work
+between lanes / ranks, the per-ray arithmetic is the same device code (reference: metrics.py:49-145,
+image_lens.py:133-178, :296-397)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(H, W, vfov_deg=40.0):
+    from light_path_tracer_b200 import image_lens as il, _device as dev
+    from light_path_tracer_b200.metrics import Schwarzschild
+    vfov = np.radians(vfov_deg)
+    fov = (2 * np.arctan(np.tan(vfov / 2) * W / H), vfov)
+    return il, dev, Schwarzschild(1.0), fov
+
+
+@pytest.mark.parametrize("dtype", ["float32", "uint8"])
+def test_interleaved_bands_equal_full_frame(native, dtype):
+    """Rank g's interleaved bands, as a compact tile and stored frame-addressed into a full frame
+    (what PeerFrame does), for widths that are and are not multiples of 32."""
+    import torch
+    from light_path_tracer_b200.dist import band_layout, band_rows_of
+    for H, W, G, target in ((216, 480, 4, 9), (216, 250, 2, 27), (96, 128, 3, 5)):
+        il, dev, metric, fov = _setup(H, W)
+        src = torch.rand(H, W, 3, device="cuda")
+        u8 = dtype == "uint8"
+        if u8:
+            src = (src * 255).to(torch.uint8)
+        full = il.render_frame(src, fov, 30.0, metric, psi=(0.03, -0.02), unit_u8=u8, flags=dev.TRACE_HYBRID | dev.TRACE_NO_REPACK)
+        b = band_layout(H, G, target)
+        assert b is not None
+        frame = torch.zeros_like(full)
+        for g in range(G):
+            row0, rows, bands, frame_rows = band_rows_of(H, g, G, b)
+            idx = torch.from_numpy(frame_rows).cuda()
+            tile = il.render_frame(src, fov, 30.0, metric, psi=(0.03, -0.02), rows=(row0, rows), bands=bands,
+                                   unit_u8=u8)
+            assert torch.equal(tile, full[idx])
+            for extra in (0, dev.RENDER_STAGED_STORES, dev.TRACE_REPACK, dev.TRACE_REPACK | dev.RENDER_STAGED_STORES):
+                il.render_frame(src, fov, 30.0, metric, psi=(0.03, -0.02), rows=(row0, rows), bands=bands,
+                                unit_u8=u8, out=frame[row0:],
+                                flags=dev.TRACE_HYBRID | dev.RENDER_OUT_FRAME_ROWS | extra)
+                assert torch.equal(frame[idx], full[idx])
+        assert torch.equal(frame, full)
+
+
+def test_staged_stores_u8(native):
+    """16-byte staged stores of 8-bit RGB tiles: full frame, ragged tile, misaligned tile."""
+    import torch
+    for H, W in ((270, 480), (101, 250)):
+        il, dev, metric, fov = _setup(H, W)
+        src = (torch.rand(H, W, 3, device="cuda") * 255).to(torch.uint8)
+        for unit in (False, True):
+            ref = il.render_frame(src, fov, 100.0, metric, unit_u8=unit)
+            out = il.render_frame(src, fov, 100.0, metric, unit_u8=unit,
+                                  flags=dev.TRACE_HYBRID | dev.RENDER_STAGED_STORES)
+            assert torch.equal(ref, out)
+            big = torch.full((H * W * 3 + 32,), 77, device="cuda", dtype=torch.uint8)
+            for shift, rows in ((0, (7, H - 20)), (1, (0, H)), (16, (3, 50))):
+                n = rows[1] * W * 3
+                view = big[shift:shift + n].view(rows[1], W, 3)
+                big.fill_(77)
+                il.render_frame(src, fov, 100.0, metric, rows=rows, out=view, unit_u8=unit,
+                                flags=dev.TRACE_HYBRID | dev.RENDER_STAGED_STORES)
+                assert torch.equal(view, ref[rows[0]:rows[0] + rows[1]])
+                assert (big[:shift] == 77).all() and (big[shift + n:] == 77).all()
+
+
+@pytest.mark.parametrize("mode", ["hybrid", "strict"])
+def test_repack_frame_bit_identical(native, mode):
+    """LP_TRACE_REPACK against the one-ray-per-thread schedule: frames, lookups and statistics,
+    over image layouts (float32 / uint8 / float64, 1 / 3 / 4 channels), zoomed and wide cameras,
+    observers near and far, ragged tiles (chunks of 256 rays that end mid-row)."""
+    import torch
+    flags0 = 4 if mode == "hybrid" else 0
+    cases = [(96, 128, 12.0, 100.0, (0.0, 0.0)),      # the smoke frame: lane efficiency 0.75 without re-packing
+             (270, 480, 40.0, 100.0, (0.02, -0.03)),
+             (301, 250, 40.0, 15.0, (0.1, 0.2)),
+             (64, 100, 3.0, 30.0, (0.0, 0.01)),       # inside the shadow edge: long, near-critical rays
+             (128, 128, 60.0, 2.9, (0.0, 0.0))]       # observer inside the photon sphere
+    for H, W, vfov_deg, r_obs, psi in cases:
+        il, dev, metric, fov = _setup(H, W, vfov_deg)
+        base = torch.rand(H, W, 4, device="cuda", dtype=torch.float64)
+        for src in (base[..., :3].float().contiguous(), (base[..., :3] * 255).to(torch.uint8).contiguous(),
+                    base[..., 0].float().contiguous(), base.contiguous(), (base * 255).to(torch.uint8).contiguous()):
+            s0, s1 = dev.new_stats(), dev.new_stats()
+            ref, fa0, w0 = il.render_frame(src, fov, r_obs, metric, psi=psi, return_lookups=True, stats=s0,
+                                           flags=flags0 | dev.TRACE_NO_REPACK)
+            out, fa1, w1 = il.render_frame(src, fov, r_obs, metric, psi=psi, return_lookups=True, stats=s1,
+                                           flags=flags0 | dev.TRACE_REPACK)
+            assert torch.equal(ref, out)
+            assert torch.equal(fa0.view(torch.int32), fa1.view(torch.int32)) and torch.equal(w0.view(torch.int16), w1.view(torch.int16))
+            a, b = dev.read_stats(s0), dev.read_stats(s1)
+            for k in ("n_rays", "n_escaped", "n_captured", "n_invalid", "n_winding", "sum_steps", "max_steps",
+                      "max_winding", "min_final_alpha", "max_final_alpha"):
+                assert a[k] == b[k], (k, a[k], b[k])
+            assert b["sum_warp_steps"] >= b["sum_steps"]
+        # row tiles whose pixel count is not a multiple of the chunk
+        src = base[..., :3].float().contiguous()
+        ref = il.render_frame(src, fov, r_obs, metric, psi=psi, flags=flags0 | dev.TRACE_NO_REPACK)
+        for rows in ((0, 1), (3, H - 5), (H - 1, 1)):
+            out = il.render_frame(src, fov, r_obs, metric, psi=psi, rows=rows, flags=flags0 | dev.TRACE_REPACK)
+            assert torch.equal(out, ref[rows[0]:rows[0] + rows[1]])
+
+
+def test_repack_1080p_and_schedule_choice(native):
+    """A full 1080p frame through the re-packing kernel equals the default schedule's frame, and
+    the per-launch predictor picks re-packing for the zoomed (divergent) frame only."""
+    import torch
+    from light_path_tracer_b200 import _lib
+    il, dev, metric, fov = _setup(1080, 1920)
+    src = torch.rand(1080, 1920, 3, device="cuda")
+    ref = il.render_frame(src, fov, 100.0, metric, flags=dev.TRACE_HYBRID | dev.TRACE_NO_REPACK)
+    assert torch.equal(ref, il.render_frame(src, fov, 100.0, metric, flags=dev.TRACE_HYBRID | dev.TRACE_REPACK))
+    assert torch.equal(ref, il.render_frame(src, fov, 100.0, metric))
+    e = _lib.ext()
+    wide = dev.camera_vector((1080, 1920), fov, (0.0, 0.0), il._psi_frame)
+    assert e.render_schedule(wide, 0, 1080, 1.0, 2.0, 100.0) is False
+    il2, _, _, fov2 = _setup(96, 128, 12.0)
+    zoom = dev.camera_vector((96, 128), fov2, (0.0, 0.0), il._psi_frame)
+    assert e.render_schedule(zoom, 0, 96, 1.0, 2.0, 100.0) is True
+
+
+def test_peer_flags_single_device(native):
+    """lp_peer_signal / lp_peer_wait on one device: a wait released by a signal issued on another
+    stream, and a wait that gives up after its timeout instead of hanging."""
+    import time
+    import torch
+    from light_path_tracer_b200 import _lib
+    e = _lib.ext()
+    flags = torch.zeros(8, dtype=torch.int64, device="cuda")
+    to = torch.zeros(1, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        e.peer_wait(flags[0:3], 3, 5, 5000, to)
+        done = torch.cuda.Event()
+        done.record()
+    time.sleep(0.05)
+    assert not done.query()                       # still spinning
+    e.peer_signal([flags.data_ptr(), flags.data_ptr() + 8, flags.data_ptr() + 16], 5, flags)
+    torch.cuda.synchronize()
+    assert done.query() and int(to.item()) == 0 and flags[:3].tolist() == [5, 5, 5]
+    t0 = time.perf_counter()
+    e.peer_wait(flags[3:4], 1, 1, 200, to)        # nobody signals flag 3
+    torch.cuda.synchronize()
+    assert 0.15 < time.perf_counter() - t0 < 3.0 and int(to.item()) == 1
