@@ -441,7 +441,7 @@ class LensPipeline:
         return render_frame(self.src, self.fov, r_obs, self.metric, psi=psi, rows=rows, stats=stats,
                             flags=flags, out=out, bands=bands, unit_u8=unit_u8)
 
-    def capture_sweep(self, params, out, flags=dev.TRACE_HYBRID, lanes=2):
+    def capture_sweep(self, params, out, flags=dev.TRACE_HYBRID, lanes=2, unit_u8=False):
         """Capture a whole parameter sweep — ``params`` = [(r_obs, psi), ...], frame j written to
         ``out[j]`` — in ONE CUDA graph and return it (``graph.replay()`` re-renders the sweep).
         Small frames are launch-bound when issued one by one from Python (a 1024x1024 frame is
@@ -455,14 +455,14 @@ class LensPipeline:
         side.wait_stream(t.cuda.current_stream())
         with t.cuda.stream(side):                       # warm-up outside the capture (module load)
             for j, (r_obs, psi) in enumerate(params[:2]):
-                self.render(r_obs, psi=psi, flags=flags, out=out[j])
+                self.render(r_obs, psi=psi, flags=flags, out=out[j], unit_u8=unit_u8)
         t.cuda.current_stream().wait_stream(side)
         graph = t.cuda.CUDAGraph()
         lanes = max(1, min(int(lanes), len(params)))
         with t.cuda.graph(graph):
             if lanes == 1:
                 for j, (r_obs, psi) in enumerate(params):
-                    self.render(r_obs, psi=psi, flags=flags, out=out[j])
+                    self.render(r_obs, psi=psi, flags=flags, out=out[j], unit_u8=unit_u8)
             else:
                 cur = t.cuda.current_stream()
                 chains = [t.cuda.Stream(device=self.src.device) for _ in range(lanes)]
@@ -470,7 +470,7 @@ class LensPipeline:
                     st.wait_stream(cur)
                 for j, (r_obs, psi) in enumerate(params):
                     with t.cuda.stream(chains[j % lanes]):
-                        self.render(r_obs, psi=psi, flags=flags, out=out[j])
+                        self.render(r_obs, psi=psi, flags=flags, out=out[j], unit_u8=unit_u8)
                 for st in chains:                         # join
                     cur.wait_stream(st)
         return graph
