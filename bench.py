@@ -449,8 +449,10 @@ def run_gpu(args):
         extra.update(multi_gpu_records(args, torch, dist, il, lpdist, dev, metric, rank, N, device, timed, barrier,
                                        max_over_ranks, checkerboard))
     if rank == 0 and N == 1:
-        extra.update(single_gpu_records(args, torch, il, dev, metric, ext, timed, src8_host, fov, H, W, flops_tile,
-                                        peak_tf, checkerboard))
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):     # the reference-facing calls print progress lines
+            extra.update(single_gpu_records(args, torch, il, dev, metric, ext, timed, src8_host, fov, H, W,
+                                            flops_tile, peak_tf, checkerboard))
 
     # ---- sums over ranks ----------------------------------------------------------------------
     if N > 1:

@@ -27,11 +27,13 @@
 // (blockIdx), CTAs are small (64 threads = 2 chunks) and back-filled by the hardware work
 // distributor exactly like lp_render_kernel's.
 #include "lp_trace.cuh"
+#include <stdlib.h>
 
 #define LP_RP_CHUNK 256
 #define LP_RP_BLOCK 64
 #define LP_RP_WARPS (LP_RP_BLOCK / 32)
 #define LP_RP_OUTQ 64
+#define LP_RP_DEFAULT_REFILL 4
 
 enum { RP_INVALID = 0, RP_ESCAPE = 1, RP_CAPTURE = 2, RP_RANOUT = 3 };
 
@@ -45,6 +47,8 @@ struct RpQueues {
     float out_a32[LP_RP_OUTQ];
     int out_k[LP_RP_OUTQ];       // step index of the exit step (RP_RANOUT: steps done so far)
     int out_code[LP_RP_OUTQ];
+    int out_tail;                // entries in the out-queue (slots are claimed with a shared-memory atomic)
+    int pad_[3];
 };
 
 // The per-ray tail for one queue entry: what binet_trace_fast4 does after its loop.
@@ -97,11 +101,20 @@ __device__ __forceinline__ void rp_finish_ray(const BinetConsts &c, const LoopRe
     if (FUSED && r.steps > retrace_steps) binet_trace<false, true>(c, L, alpha, r);     // LP_TRACE_HYBRID
 }
 
+// per-warp frame statistics (shared memory; filled by warp reductions in the finish phase so that
+// no accumulator lives in registers across the RK4 loop)
+struct RpStats {
+    unsigned long long sum_steps, min_fa, max_fa;     // min/max as ordered bit patterns (dbl_to_ordered)
+    unsigned int n_rays, escaped, captured, invalid, winding, max_steps, max_winding, trips;
+};
+
 template <bool FUSED, typename T, int MINB>
 __global__ void __launch_bounds__(LP_RP_BLOCK, MINB)
-lp_render_repack_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts c, const CamConsts cam)
+lp_render_repack_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts c, const CamConsts cam,
+                        const int refill_min)
 {
     extern __shared__ __align__(16) unsigned char rp_smem[];
+    __shared__ RpStats rp_stats[LP_RP_WARPS];
     const LoopRegs L = load_loop_regs(c);
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     const unsigned full = 0xffffffffu;
@@ -110,77 +123,93 @@ lp_render_repack_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts
     const size_t stage_bytes = ((size_t)LP_RP_CHUNK * C * sizeof(T) + 15) & ~(size_t)15;
     RpQueues &q = *reinterpret_cast<RpQueues *>(rp_smem + (size_t)wrp * (sizeof(RpQueues) + stage_bytes));
     T *stage = reinterpret_cast<T *>(rp_smem + (size_t)wrp * (sizeof(RpQueues) + stage_bytes) + sizeof(RpQueues));
+    RpStats &ws = rp_stats[wrp];
+    if (lane == 0) {
+        q.out_tail = 0;
+        ws.sum_steps = 0ull; ws.min_fa = ~0ull; ws.max_fa = 0ull;
+        ws.n_rays = ws.escaped = ws.captured = ws.invalid = ws.winding = ws.max_steps = ws.max_winding = ws.trips = 0u;
+    }
+    __syncwarp();
 
     const long long chunk0 = ((long long)blockIdx.x * LP_RP_WARPS + wrp) * LP_RP_CHUNK;   // first pixel of the chunk
     const int n_chunk = (int)min((long long)LP_RP_CHUNK, a.n - chunk0);                  // <= 0: nothing to do
     const int n_batches = n_chunk > 0 ? (n_chunk + 31) / 32 : 0;
 
-    StatAcc acc;
-    acc.init();
-    unsigned long long n_rays_thread = 0ull;
-
-    // lane state
-    bool has = false;
+    // lane state.  code: -2 no ray, -1 integrating
+    int code = -2;
     double u = 0.0, w = 0.0;
     int k = 0, pix = 0;
     float a32 = 0.0f;
     // warp-uniform queue state (every lane derives the same values from ballots)
     int in_head = 0, in_count = 0, out_count = 0, next_batch = 0;
-    int trips = 0;               // loop trips of this warp (4 RK4 steps x 32 lanes each)
 
     const double M3 = L.M3, h = L.h, hh = L.hh, h6 = L.h6;
     const unsigned lo_hi = L.lo_hi, span = L.span;
     const int n_full = L.n_full;
 
-    // the per-ray tail for `cnt` queued exit states (the LAST cnt entries of the out-queue), all lanes together
-    auto finish_batch = [&](int cnt) {
-        const int e = out_count - cnt + lane;
-        const bool mine = lane < cnt;
-        RayResult r;
-        r.status = 0; r.steps = 0; r.nh = 0; r.fa = 0.0;
-        if (mine) {
-            const int p = q.out_pix[e];
-            const float al = q.out_a32[e];
-            rp_finish_ray<FUSED>(c, L, q.out_code[e], q.out_k[e], q.out_up[e], q.out_wp[e], q.out_u[e], q.out_w[e],
-                                 (double)al, a.retrace_steps, r);
-            const long long i = chunk0 + p;
-            int row, col;
-            long long oi;
-            tile_pixel(a, cam.width, i, row, col, oi);
-            const float fa32 = (float)((r.status == 1) ? r.fa : __longlong_as_double(0x7ff8000000000000LL));
-            const long long nh = r.nh < 0 ? 0 : (r.nh > 65535 ? 65535 : r.nh);
-            if (a.out_fa) ((float *)a.out_fa)[i] = fa32;
-            if (a.out_w) ((unsigned short *)a.out_w)[i] = (unsigned short)nh;
-            remap_pixel<T>(ra, cam, stage + (size_t)p * C, row, col, fa32, (unsigned)nh);
-            n_rays_thread++;
+    // Each phase appears ONCE in the code (the kernel is instruction-cache sensitive: the finish
+    // phase with its strict re-trace is ~5 k instructions).  Capacity of the out-queue: exit
+    // states are pushed (<= 32 at a time) and invalid rays prepared (<= 32) only while fewer than
+    // 32 are queued -> never more than 63 of 64.
+    while (true) {
+        // ---- finish: 32 gathered exit states, or whatever is left when the chunk has drained ----
+        const bool rays_left = in_count > 0 || next_batch < n_batches;
+        const bool any_ray = __ballot_sync(full, code != -2) != 0u;
+        if (out_count >= 32 || (!rays_left && !any_ray && out_count > 0)) {
+            const int cnt = min(out_count, 32);
+            const int e = out_count - cnt + lane;
+            const bool mine = lane < cnt;
+            RayResult r;
+            r.status = 0; r.steps = 0; r.nh = 0; r.fa = 0.0;
+            if (mine) {
+                const int p = q.out_pix[e];
+                const float al = q.out_a32[e];
+                rp_finish_ray<FUSED>(c, L, q.out_code[e], q.out_k[e], q.out_up[e], q.out_wp[e], q.out_u[e], q.out_w[e],
+                                     (double)al, a.retrace_steps, r);
+                const long long i = chunk0 + p;
+                int row, col;
+                long long oi;
+                tile_pixel(a, cam.width, i, row, col, oi);
+                const float fa32 = (float)((r.status == 1) ? r.fa : __longlong_as_double(0x7ff8000000000000LL));
+                const long long nh = r.nh < 0 ? 0 : (r.nh > 65535 ? 65535 : r.nh);
+                if (a.out_fa) ((float *)a.out_fa)[i] = fa32;
+                if (a.out_w) ((unsigned short *)a.out_w)[i] = (unsigned short)nh;
+                remap_pixel<T>(ra, cam, stage + (size_t)p * C, row, col, fa32, (unsigned)nh);
+            }
+            if (a.stats) {
+                const unsigned st = mine ? (unsigned)r.steps : 0u;
+                const unsigned nhc = mine ? (unsigned)(r.nh < 0 ? 0 : (r.nh > 65535 ? 65535 : r.nh)) : 0u;
+                const bool esc = mine && r.status == 1;
+                const unsigned s_sum = __reduce_add_sync(full, st), s_max = __reduce_max_sync(full, st);
+                const unsigned w_max = __reduce_max_sync(full, nhc);
+                const unsigned n_esc = __popc(__ballot_sync(full, esc));
+                const unsigned n_cap = __popc(__ballot_sync(full, mine && r.status == -1));
+                const unsigned n_inv = __popc(__ballot_sync(full, mine && r.status == 0));
+                const unsigned n_win = __popc(__ballot_sync(full, esc && (float)r.fa > LP_HALF_PI_F32));
+                unsigned long long mn = (esc && r.fa == r.fa) ? dbl_to_ordered(r.fa) : ~0ull;
+                unsigned long long mx = (esc && r.fa == r.fa) ? dbl_to_ordered(r.fa) : 0ull;
+                for (int off = 16; off > 0; off >>= 1) {
+                    mn = min(mn, __shfl_xor_sync(full, mn, off));
+                    mx = max(mx, __shfl_xor_sync(full, mx, off));
+                }
+                if (lane == 0) {
+                    ws.sum_steps += s_sum; ws.max_steps = max(ws.max_steps, s_max);
+                    ws.max_winding = max(ws.max_winding, w_max);
+                    ws.n_rays += (unsigned)cnt; ws.escaped += n_esc; ws.captured += n_cap; ws.invalid += n_inv;
+                    ws.winding += n_win; ws.min_fa = min(ws.min_fa, mn); ws.max_fa = max(ws.max_fa, mx);
+                }
+            }
+            out_count -= cnt;
+            if (lane == 0) q.out_tail = out_count;
+            __syncwarp();
+            continue;
         }
-        if (a.stats && mine) {
-            acc.sum_steps += (unsigned)r.steps;
-            acc.max_steps = max(acc.max_steps, (unsigned)r.steps);
-            const long long nhc = r.nh < 0 ? 0 : (r.nh > 65535 ? 65535 : r.nh);
-            acc.max_winding = max(acc.max_winding, (unsigned)nhc);
-            if (r.status == 1) {
-                acc.escaped++;
-                if ((float)r.fa > LP_HALF_PI_F32) acc.winding++;
-                acc.min_fa = fmin(acc.min_fa, r.fa);
-                acc.max_fa = fmax(acc.max_fa, r.fa);
-            } else if (r.status == -1) acc.captured++;
-            else acc.invalid++;
-        }
-        out_count -= cnt;
-        __syncwarp();
-    };
+        if (!rays_left && !any_ray) break;
 
-    // One iteration = (refill) -> (one trip + push) -> (finish when 32 exit states have gathered).
-    // Each phase appears ONCE in the code (the kernel is instruction-cache sensitive: the tail
-    // with its strict re-trace is ~5 k instructions).  Capacity: prepare and push only run with
-    // fewer than 32 queued exit states and add at most 32 each -> never more than 63 of 64.
-    bool done = false;
-    while (!done) {
-        // ---- refill: idle lanes pop prepared rays; prepare the next 32 pixels when none are left ----
-        const unsigned need = __ballot_sync(full, !has);
-        if (need && out_count < 32) {
-            if (in_count == 0 && next_batch < n_batches) {
+        // ---- refill: lanes without a ray pop prepared rays; prepare the next 32 pixels when none are left ----
+        const unsigned need = __ballot_sync(full, code == -2);
+        if (need && rays_left) {
+            if (in_count == 0) {
                 // per-ray head of batch `next_batch`, all lanes together
                 const int p = next_batch * 32 + lane;
                 next_batch++;
@@ -209,28 +238,34 @@ lp_render_repack_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts
                 in_head = 0;
                 in_count = __popc(vm);
                 out_count += __popc(im);
+                if (lane == 0) q.out_tail = out_count;
                 __syncwarp();
+                if (in_count == 0) continue;             // nothing valid in this batch (may have to finish first)
             }
-            if (in_count > 0) {
-                const int rank = __popc(need & lt_mask);
-                if (!has && rank < in_count) {
-                    const int s = in_head + rank;
-                    w = q.in_w0[s]; pix = q.in_pix[s]; a32 = q.in_a32[s];
-                    u = c.u0; k = 0; has = true;
-                }
-                const int taken = min(__popc(need), in_count);
-                in_head += taken;
-                in_count -= taken;
-                __syncwarp();
+            const int rank = __popc(need & lt_mask);
+            if (code == -2 && rank < in_count) {
+                const int s = in_head + rank;
+                w = q.in_w0[s]; pix = q.in_pix[s]; a32 = q.in_a32[s];
+                u = c.u0; k = 0; code = -1;
             }
+            const int taken = min(__popc(need), in_count);
+            in_head += taken;
+            in_count -= taken;
+            __syncwarp();
+            // lanes may still be empty (the in-queue ran dry): go round again unless nothing is left
+            if (__ballot_sync(full, code == -2) != 0u && (in_count > 0 || next_batch < n_batches)) continue;
         }
 
-        // ---- one trip: four RK4 steps, one exit test (binet_trace_fast4's loop body) ----
-        if (out_count < 32 && __ballot_sync(full, has) != 0u) {
-            int code = -1;                  // -1: still inside the band
-            double up = 0.0, wp = 0.0;
-            int kx = 0;
-            if (has) {
+        // ---- integrate: trips of four RK4 steps (binet_trace_fast4's loop body) until enough lanes have left
+        // the band to make a refill worth its bookkeeping (refill_min; everything, once no ray is left to pop) ----
+        // A lane that leaves the band claims a slot of the out-queue (shared-memory atomic) and stores its raw
+        // exit state there at once — nothing but (u, w, k) stays live across trips.
+        const int stop_at = (in_count > 0 || next_batch < n_batches) ? refill_min : 32;
+        unsigned idle;
+        do {
+            if (code == -1) {
+                double up, wp;
+                int xcode = -1;
                 if (k + 4 <= n_full) {
                     double u1, w1, u2, w2, u3, w3, u4, w4;
                     rk4_step<FUSED>(u, w, M3, h, hh, h6, u1, w1);
@@ -255,36 +290,28 @@ lp_render_repack_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts
                     }
                     if (which == 0) { u = u4; w = w4; k += 4; }
                     else {
-                        code = cap ? RP_CAPTURE : RP_ESCAPE;
-                        kx = k + which - 1;
+                        xcode = cap ? RP_CAPTURE : RP_ESCAPE;
+                        k += which - 1;                     // index of the exit step
                         if (which == 1) { up = u; wp = w; u = u1; w = w1; }
                         else if (which == 2) { up = u1; wp = w1; u = u2; w = w2; }
                         else if (which == 3) { up = u2; wp = w2; u = u3; w = w3; }
                         else { up = u3; wp = w3; u = u4; w = w4; }
                     }
                 } else {
-                    code = RP_RANOUT; kx = k;       // fewer than four full steps left: finished in the tail
+                    xcode = RP_RANOUT; up = u; wp = w;      // fewer than four full steps left: finished in the tail
                 }
-            }
-            trips++;
-            // ---- push exit states ----
-            const unsigned ex = __ballot_sync(full, code >= 0);
-            if (ex) {
-                if (code >= 0) {
-                    const int s = out_count + __popc(ex & lt_mask);
+                if (xcode >= 0) {
+                    const int s = atomicAdd(&q.out_tail, 1);
                     q.out_up[s] = up; q.out_wp[s] = wp; q.out_u[s] = u; q.out_w[s] = w;
-                    q.out_pix[s] = pix; q.out_a32[s] = a32; q.out_k[s] = kx; q.out_code[s] = code;
-                    has = false;
+                    q.out_pix[s] = pix; q.out_a32[s] = a32; q.out_k[s] = k; q.out_code[s] = xcode;
+                    code = -2;
                 }
-                out_count += __popc(ex);
-                __syncwarp();
             }
-        }
-
-        // ---- finish: 32 gathered exit states, or whatever is left when the chunk has drained ----
-        const bool more = __ballot_sync(full, has) != 0u || in_count > 0 || next_batch < n_batches;
-        if (out_count >= 32 || (!more && out_count > 0)) finish_batch(min(out_count, 32));
-        done = !more && out_count == 0;
+            if (a.stats && lane == 0) ws.trips++;
+            idle = __ballot_sync(full, code != -1);
+        } while (__popc(idle) < stop_at);
+        __syncwarp();
+        out_count = *(volatile int *)&q.out_tail;
     }
 
     // ---- write-out of the chunk's pixels ----
@@ -310,8 +337,18 @@ lp_render_repack_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts
         }
     }
     if (a.stats) {
-        if (lane == 0) acc.warp_steps = 128ull * (unsigned)trips;
-        lp_stats_flush(acc, n_rays_thread, a.stats);
+        StatAcc acc;
+        acc.init();
+        unsigned long long n_rays = 0ull;
+        if (lane == 0) {
+            acc.escaped = ws.escaped; acc.captured = ws.captured; acc.invalid = ws.invalid; acc.winding = ws.winding;
+            acc.max_steps = ws.max_steps; acc.max_winding = ws.max_winding; acc.sum_steps = ws.sum_steps;
+            acc.warp_steps = 128ull * ws.trips;
+            acc.min_fa = __longlong_as_double((long long)ws.min_fa);
+            acc.max_fa = __longlong_as_double((long long)ws.max_fa);
+            n_rays = ws.n_rays;
+        }
+        lp_stats_flush(acc, n_rays, a.stats);
     }
 }
 
@@ -334,8 +371,16 @@ static int launch_repack_t(const TraceArgs &a, const RemapArgs &ra, const BinetC
         cudaGetLastError();
         return LP_ERR_UNSUPPORTED;
     }
-    if (fused) kf<<<(unsigned)ctas, LP_RP_BLOCK, smem, stream>>>(a, ra, c, cam);
-    else       ks<<<(unsigned)ctas, LP_RP_BLOCK, smem, stream>>>(a, ra, c, cam);
+    // idle lanes that trigger a refill (LP_REPACK_REFILL = 1..32, tuning knob: 1 = refill after every trip
+    // that saw an exit; larger values trade idle lanes for less bookkeeping)
+    static int refill = 0;
+    if (!refill) {
+        const char *e = getenv("LP_REPACK_REFILL");
+        const int v = e ? atoi(e) : 0;
+        refill = (v >= 1 && v <= 32) ? v : LP_RP_DEFAULT_REFILL;
+    }
+    if (fused) kf<<<(unsigned)ctas, LP_RP_BLOCK, smem, stream>>>(a, ra, c, cam, refill);
+    else       ks<<<(unsigned)ctas, LP_RP_BLOCK, smem, stream>>>(a, ra, c, cam, refill);
     return lp_check_launch();
 }
 

@@ -211,6 +211,10 @@ class PeerFrame:
         self.handle = symm_mem.rendezvous(self.buf, self.group)
         self.pad_handle = symm_mem.rendezvous(self.pad, self.group)
         self.pad.zero_()
+        # load the two flag kernels NOW (CUDA loads kernels lazily and a load may wait for the device to drain:
+        # it must never happen while a wait kernel is spinning on this GPU)
+        self._ext.peer_signal([int(self.pad.data_ptr()) + 8 * 48], 1, self.pad)
+        self._ext.peer_wait(self.pad[48:49], 1, 1, 1000, None)
         torch.cuda.synchronize(device)
         dist.barrier(group=self.group)                 # every pad is zero before anybody signals
         frame_numel = self.height * int(np.prod(self.row_shape))

@@ -134,7 +134,12 @@ def test_peer_flags_single_device(native):
     e = _lib.ext()
     flags = torch.zeros(8, dtype=torch.int64, device="cuda")
     to = torch.zeros(1, dtype=torch.int32, device="cuda")
+    # first launches load the two kernels (CUDA loads lazily, and a load can wait for the device to
+    # drain: it must not happen while a wait kernel is spinning — PeerFrame warms them the same way)
+    e.peer_signal([flags.data_ptr() + 56], 1, flags)
+    e.peer_wait(flags[7:8], 1, 1, 1000, to)
     torch.cuda.synchronize()
+    assert int(to.item()) == 0
     side = torch.cuda.Stream()
     with torch.cuda.stream(side):
         e.peer_wait(flags[0:3], 3, 5, 5000, to)
