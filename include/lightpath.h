@@ -45,15 +45,14 @@ extern "C" {
                                      reference's order (bit-identical u, w, phi)   */
 #define LP_TRACE_FUSED      1u    /* allow FMA contraction inside the RK4 step
                                      (faster, ulp-level different trajectories)     */
-#define LP_TRACE_REPACK     2u    /* lp_render_frame / lp_schw_trace_frame: force the lane
-                                     re-packing schedule (persistent warps; a lane whose ray has
-                                     left the integration band hands it to the warp's result
-                                     queue and takes the next prepared ray, so captured / escaped
-                                     rays stop wasting lanes).  Same results bit for bit.  Without
-                                     this flag (and without LP_TRACE_NO_REPACK) the library picks
-                                     the schedule per launch from the frame geometry (see
-                                     lp_render_schedule)                                     */
-#define LP_TRACE_NO_REPACK  32u   /* force the one-ray-per-thread schedule                   */
+#define LP_TRACE_REPACK     2u    /* lp_render_frame: opt-in lane re-packing schedule (persistent
+                                     warps; a lane whose ray has left the integration band hands it to
+                                     the warp's result queue and takes the next prepared ray, so
+                                     captured / escaped rays stop wasting lanes).  Same frame bit for
+                                     bit.  NOT the default: measured on B200 it is slower than the
+                                     one-ray-per-thread kernel on every frame tried, including the
+                                     divergent ones (profiles/r2b_repack_perf_refill_sweep.log) — the
+                                     default keeps divergence down with 8x4-pixel warp tiles instead */
 #define LP_TRACE_HYBRID     4u    /* FMA-contracted loop for rays that finish within 12 rad
                                      of swept angle (240 RK4 steps at h = 0.05; they stay
                                      within 1e-11 of the strict result), strict re-trace of
@@ -231,11 +230,6 @@ int lp_render_frame_bands(const void *src, int32_t src_dtype, int32_t channels,
                           void *out, float *out_fa32, uint16_t *out_w16,
                           lp_frame_stats *stats, uint32_t flags, void *stream);
 
-/* Which schedule lp_render_frame would pick for this frame without LP_TRACE_REPACK /
- * LP_TRACE_NO_REPACK: 1 = lane re-packing, 0 = one ray per thread.  Host arithmetic only. */
-int lp_render_schedule(const lp_camera *h_cam, int32_t row0, int32_t rows,
-                       double M, double R_S, double r_obs, int32_t *repack);
-
 /* ---- peer-memory completion flags (multi-GPU frame assembly) -------------
  * Row tiles are stored by every rank's render kernel straight into the root GPU's frame
  * through NVLink peer mappings; these two stream-ordered calls order "all tiles of frame e
@@ -336,6 +330,23 @@ int lp_kerr_rk45_integrate_paths(const double *state0, int64_t n,
                                  double *out_state, double *out_lambda,
                                  int8_t *out_outcome, int32_t *out_nsteps, int8_t *out_status,
                                  void *stream);
+
+/* Trajectories WITH their dense output — what solve_ivp(dense_output=True) keeps for
+ * OdeResult.sol (geodesic_tracer.py:57-67; scipy rk.py:178-180, :715-737).  As the *_paths entry
+ * points above plus dense[n][max_points][25]: row k >= 1 holds (h, Q[6][4]) of the accepted step
+ * that ended in point k, Q = K^T P for the six moving components (t, r, theta, phi, p_r, p_theta;
+ * p_t and p_phi are constants of the motion, their rows of Q are exactly zero):
+ *     sol(t) = y_old + h * Q @ (x, x^2, x^3, x^4),  x = (t - t_old) / h.
+ * Exactly one of alphas / state0 is given.  metric 0 = Schwarzschild (a ignored, R_S_or_r_plus =
+ * R_S), 1 = Kerr (R_S_or_r_plus = r_plus; state0 only). */
+int lp_rk45_paths_dense(int32_t metric, const double *alphas, const double *state0, int64_t n,
+                        double M, double a, double R_S_or_r_plus, double r_obs,
+                        double lambda_max, double rtol, double atol, double max_step,
+                        double r_stop_inner, double r_stop_outer,
+                        double *traj, int32_t max_points, int32_t *n_points, double *dense,
+                        double *out_state, double *out_lambda,
+                        int8_t *out_outcome, int32_t *out_nsteps, int8_t *out_status,
+                        void *stream);
 
 /* ---- Kerr tracer (next row after the Schwarzschild path) ------ */
 

@@ -33,8 +33,7 @@ H_MAX = 0.05     # metrics.py:833 (and :824 for the scalar path)
 TRACE_STRICT = 0
 TRACE_FUSED = 1
 RENDER_STAGED_STORES = 8   # lp_render_frame: 16-byte staged pixel stores (peer-memory tiles)
-TRACE_REPACK = 2            # force the lane re-packing schedule (lp_repack.cu)
-TRACE_NO_REPACK = 32        # force one ray per thread (default: chosen per launch from the geometry)
+TRACE_REPACK = 2            # opt-in lane re-packing schedule (lp_repack.cu); the default is one ray per thread
 RENDER_OUT_FRAME_ROWS = 16  # interleaved-band tile stored at its frame rows (peer frames)
 TRACE_HYBRID = 4   # FMA loop + strict re-trace of rays longer than 240 steps (lightpath.h)
 

@@ -59,7 +59,6 @@ SYMBOLS = {
                                        _I32, _I32, _VP, _VP, _VP, _VP, _U32, _VP]),
     "lp_render_frame_bands": (ctypes.c_int, [_VP, _I32, _I32, _CAMP, _I32, _I32, _I32, _I32, _D, _D, _D, _D, _D,
                                              _I32, _I32, _VP, _VP, _VP, _VP, _U32, _VP]),
-    "lp_render_schedule": (ctypes.c_int, [_CAMP, _I32, _I32, _D, _D, _D, _VP]),
     "lp_peer_signal": (ctypes.c_int, [_VP, _I32, ctypes.c_uint64, _VP]),
     "lp_peer_wait": (ctypes.c_int, [_VP, _I32, ctypes.c_uint64, _U32, _VP, _VP]),
     "lp_shadow_classify": (ctypes.c_int, [_I32, _I32, _D, _D, _VP, _VP, _VP]),
@@ -73,6 +72,8 @@ SYMBOLS = {
                                                     _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "lp_kerr_rk45_integrate_paths": (ctypes.c_int, [_VP, _I64, _D, _D, _D, _D, _D, _D, _D, _D, _D, _VP, _I32,
                                                     _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "lp_rk45_paths_dense": (ctypes.c_int, [_I32, _VP, _VP, _I64, _D, _D, _D, _D, _D, _D, _D, _D, _D, _D, _VP, _I32,
+                                           _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "lp_kerr_trace_batch_f64": (ctypes.c_int, [_VP, _VP, _VP, _I64, _D, _D, _D, _D, _D, _D, _VP, _VP, _VP, _VP, _VP]),
     "lp_kerr_trace_alpha32": (ctypes.c_int, [_VP, _CAMP, _I32, _I32, _VP, _D, _D, _D, _D, _D, _D, _VP, _VP, _VP,
                                              _VP, _VP]),

@@ -73,6 +73,8 @@ struct Rk45Args {
     double *traj;               // optional [n][max_points][9]
     int32_t max_points;
     int32_t *n_points;          // optional [n]
+    double *dense;              // optional [n][max_points][25]: row k >= 1 = (h, Q[6][4]) of the accepted step
+                                // that ended in point k — scipy's RkDenseOutput (rk.py:178-180, :715-737)
     int32_t refill_min;         // lanes that must be waiting before a flush (RK_REFILL_MIN)
 };
 
@@ -256,7 +258,7 @@ __device__ __forceinline__ void rk_f<1>(const Rk45Args &a, double r_floor, doubl
     rk_rhs_kerr(a.kerr_M, a.kerr_a, r_floor, p_t, p_phi, y, tc, d);
 }
 
-template <int MINB, int METRIC>
+template <int MINB, int METRIC, bool DENSE = false>
 __global__ void __launch_bounds__(RK_BLOCK, MINB)
 lp_rk45_kernel(const Rk45Args a)
 {
@@ -500,6 +502,21 @@ lp_rk45_kernel(const Rk45Args a)
                     }
                 }
                 g0 = gn0; g1 = gn1;
+                if (DENSE && a.dense && npts < a.max_points) {
+                    // the step's interpolant for OdeResult.sol: h and Q = K^T P (rk.py:178-180)
+                    double *row = a.dense + ((size_t)idx * a.max_points + npts) * 25;
+                    row[0] = h;
+#pragma unroll
+                    for (int i = 0; i < RK_NC; ++i) {
+#pragma unroll
+                        for (int m = 0; m < 4; ++m) {
+                            double acc = K[0][i] * c_P[0][m];
+#pragma unroll
+                            for (int j = 2; j < 7; ++j) acc = fma(K[j][i], c_P[j][m], acc);
+                            row[1 + 4 * i + m] = acc;
+                        }
+                    }
+                }
                 write_point(a, idx, npts, t_fin, yf, p_t, p_phi);
                 npts++;
                 t = t_new;
@@ -534,7 +551,8 @@ static int rk45_launch(bool metric_is_kerr, double kerr_a, const double *alphas,
                        double r_stop_inner, double r_stop_outer,
                        double *out_state, double *out_lambda, int8_t *out_outcome,
                        int32_t *out_nsteps, int8_t *out_status,
-                       double *traj, int32_t max_points, int32_t *n_points, cudaStream_t stream)
+                       double *traj, int32_t max_points, int32_t *n_points, cudaStream_t stream,
+                       double *dense = nullptr)
 {
     (void)M;
     if (n < 0 || max_points < 0) return LP_ERR_INVALID_ARG;
@@ -555,7 +573,7 @@ static int rk45_launch(bool metric_is_kerr, double kerr_a, const double *alphas,
     a.sqrt_f0 = sqrt(a.f0);
     a.out_state = out_state; a.out_lambda = out_lambda; a.out_outcome = out_outcome;
     a.out_nsteps = out_nsteps; a.out_status = out_status;
-    a.traj = traj; a.max_points = max_points; a.n_points = n_points;
+    a.traj = traj; a.max_points = max_points; a.n_points = n_points; a.dense = dense;
     // resident CTAs per SM ptxas must fit: 2 -> 202 registers, no spills; 3 -> 168; 4 -> 128 (spills).
     // LP_RK45_MINB selects (tuning knob); the default is the measured best (4K frame: 2 -> 184 ms,
     // 3 -> 154 ms, 4 -> 164 ms: the kernel is bound by the latency of the right-hand side's dependent
@@ -574,6 +592,17 @@ static int rk45_launch(bool metric_is_kerr, double kerr_a, const double *alphas,
     }
     a.refill_min = refill;
     const bool kerr = metric_is_kerr;
+    if (dense) {            // single-ray API (OdeResult.sol): the variant that also stores every step's interpolant
+        const void *fd = kerr ? (const void *)lp_rk45_kernel<2, 1, true> : (const void *)lp_rk45_kernel<2, 0, true>;
+        int gd = 0;
+        int rcd = lp_grid_for(fd, RK_BLOCK, &gd);
+        if (rcd != LP_OK) return rcd;
+        const long long ch = (n + RK_BLOCK - 1) / RK_BLOCK;
+        if (ch < gd) gd = (int)ch;
+        if (kerr) lp_rk45_kernel<2, 1, true><<<gd, RK_BLOCK, 0, stream>>>(a);
+        else lp_rk45_kernel<2, 0, true><<<gd, RK_BLOCK, 0, stream>>>(a);
+        return lp_check_launch();
+    }
     const void *fn = kerr ? (const void *)lp_rk45_kernel<2, 1>
                    : minb == 2 ? (const void *)lp_rk45_kernel<2, 0>
                    : minb == 3 ? (const void *)lp_rk45_kernel<3, 0> : (const void *)lp_rk45_kernel<4, 0>;
@@ -648,4 +677,30 @@ extern "C" int lp_kerr_rk45_integrate_paths(const double *state0, int64_t n,
     return rk45_launch(true, a, nullptr, state0, n, M, r_plus, 4.0 * r_plus, lambda_max, rtol, atol, max_step,
                        r_stop_inner, r_stop_outer, out_state, out_lambda, out_outcome, out_nsteps, out_status,
                        traj, max_points, n_points, (cudaStream_t)stream);
+}
+
+// Trajectories WITH their dense output (what solve_ivp(dense_output=True) keeps for OdeResult.sol,
+// geodesic_tracer.py:57-67): as the *_paths entry points above, plus dense[n][max_points][25] —
+// row k >= 1 holds (h, Q[6][4]) of the accepted step that ended in point k, Q = K^T P restricted
+// to the six moving components (t, r, theta, phi, p_r, p_theta; p_t and p_phi are constants of
+// the motion: their rows of Q are exactly zero).  sol(t) = y_old + h * Q @ (x, x^2, x^3, x^4),
+// x = (t - t_old) / h (rk.py:723-737).  Exactly one of alphas / state0 is given; metric 0 =
+// Schwarzschild (a ignored, R_S_or_r_plus = R_S), 1 = Kerr (R_S_or_r_plus = r_plus, state0 only).
+extern "C" int lp_rk45_paths_dense(int32_t metric, const double *alphas, const double *state0, int64_t n,
+                                   double M, double a, double R_S_or_r_plus, double r_obs,
+                                   double lambda_max, double rtol, double atol, double max_step,
+                                   double r_stop_inner, double r_stop_outer,
+                                   double *traj, int32_t max_points, int32_t *n_points, double *dense,
+                                   double *out_state, double *out_lambda,
+                                   int8_t *out_outcome, int32_t *out_nsteps, int8_t *out_status,
+                                   void *stream)
+{
+    if (metric != 0 && metric != 1) return LP_ERR_INVALID_ARG;
+    if ((alphas != nullptr) == (state0 != nullptr)) return LP_ERR_INVALID_ARG;
+    if (metric == 1 && alphas) return LP_ERR_UNSUPPORTED;
+    if (n > 0 && (!traj || !n_points || !dense || max_points < 1)) return LP_ERR_INVALID_ARG;
+    const double r_obs_used = alphas ? r_obs : 4.0 * R_S_or_r_plus;      // only feeds initial_conditions
+    return rk45_launch(metric == 1, a, alphas, state0, n, M, R_S_or_r_plus, r_obs_used, lambda_max, rtol, atol,
+                       max_step, r_stop_inner, r_stop_outer, out_state, out_lambda, out_outcome, out_nsteps,
+                       out_status, traj, max_points, n_points, (cudaStream_t)stream, dense);
 }

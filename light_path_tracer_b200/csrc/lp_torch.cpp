@@ -171,14 +171,6 @@ void render_frame(const Tensor &src, int64_t channels, const std::vector<double>
           "lp_render_frame_bands");
 }
 
-bool render_schedule(const std::vector<double> &camv, int64_t row0, int64_t rows, double M, double R_S, double r_obs)
-{
-    lp_camera cam = make_cam(camv);
-    int32_t repack = 0;
-    check(lp_render_schedule(&cam, (int32_t)row0, (int32_t)rows, M, R_S, r_obs, &repack), "lp_render_schedule");
-    return repack != 0;
-}
-
 // flag_ptrs: raw device addresses (possibly peer-mapped) as integers; stream = current stream of `device_of`
 void peer_signal(const std::vector<int64_t> &flag_ptrs, int64_t value, const Tensor &device_of)
 {
@@ -303,6 +295,29 @@ void kerr_rk45_integrate_paths(const Tensor &state0, double M, double a, double 
           "lp_kerr_rk45_integrate_paths");
 }
 
+void rk45_paths_dense(int64_t metric, OptTensor alphas, OptTensor state0, double M, double a, double rs, double r_obs,
+                      double lambda_max, double rtol, double atol, double max_step, double r_in, double r_out,
+                      Tensor traj, int64_t max_points, Tensor n_points, Tensor dense, Tensor out_state,
+                      Tensor out_lambda, Tensor out_outcome, Tensor out_nsteps, Tensor out_status)
+{
+    const bool by_alpha = alphas.has_value() && alphas->defined();
+    const Tensor &in = by_alpha ? *alphas : *state0;
+    const int64_t n = by_alpha ? in.numel() : in.numel() / 8;
+    c10::cuda::CUDAGuard g(in.device());
+    check(lp_rk45_paths_dense((int32_t)metric, (const double *)optptr(alphas, c10::ScalarType::Double, "alphas", 0),
+                              (const double *)optptr(state0, c10::ScalarType::Double, "state0", 0), n, M, a, rs, r_obs,
+                              lambda_max, rtol, atol, max_step, r_in, r_out,
+                              (double *)ptr(traj, c10::ScalarType::Double, "traj", n * max_points * 9),
+                              (int32_t)max_points, (int32_t *)ptr(n_points, c10::ScalarType::Int, "n_points", n),
+                              (double *)ptr(dense, c10::ScalarType::Double, "dense", n * max_points * 25),
+                              (double *)ptr(out_state, c10::ScalarType::Double, "out_state", 8 * n),
+                              (double *)ptr(out_lambda, c10::ScalarType::Double, "out_lambda", n),
+                              (int8_t *)ptr(out_outcome, c10::ScalarType::Char, "out_outcome", n),
+                              (int32_t *)ptr(out_nsteps, c10::ScalarType::Int, "out_nsteps", 2 * n),
+                              (int8_t *)ptr(out_status, c10::ScalarType::Char, "out_status", n), stream_of(in)),
+          "lp_rk45_paths_dense");
+}
+
 void kerr_trace_batch(const Tensor &alphas, const Tensor &thetas, OptTensor refine, double M, double a, double r_plus,
                       double r_obs, double theta_obs, double lambda_max, Tensor out_fa, Tensor out_w,
                       OptTensor status, OptTensor steps)
@@ -376,7 +391,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
           py::arg("loop_around"), py::arg("sampling"), py::arg("out"), py::arg("fa32"), py::arg("w16"),
           py::arg("stats"), py::arg("flags"), py::arg("unit_u8"), py::arg("band_rows") = 0,
           py::arg("band_stride") = 0);
-    m.def("render_schedule", &render_schedule);
     m.def("peer_signal", &peer_signal);
     m.def("peer_wait", &peer_wait);
     m.def("shadow_classify", &shadow_classify);
@@ -386,6 +400,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.def("rk45_trace_paths", &rk45_trace_paths);
     m.def("rk45_integrate_paths", &rk45_integrate_paths);
     m.def("kerr_rk45_integrate_paths", &kerr_rk45_integrate_paths);
+    m.def("rk45_paths_dense", &rk45_paths_dense);
     m.def("kerr_trace_batch", &kerr_trace_batch);
     m.def("kerr_trace_alpha32", &kerr_trace_alpha32);
     m.def("bench_dfma", &bench_dfma);

@@ -11,6 +11,7 @@
 #include <stdlib.h>
 
 #define LP_RENDER_DEFAULT_TRIP 4
+#define LP_RENDER_DEFAULT_TILE_H 4
 #define LP_TRACE_DEFAULT_BLOCK 64   /* rays per CTA; LP_TRACE_BLOCK=32|64|128|256 overrides (tuning) */
 
 // LP_TRACE_HYBRID threshold.  The FMA-contracted loop differs from the strict one by ~1e-16
@@ -191,37 +192,51 @@ lp_render_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts c, con
     const LoopRegs L = load_loop_regs(c);
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < a.n;
-    // RGB (float32 or 8-bit) into a 16-byte aligned tile: a full warp's 32 pixels (384 / 96
-    // contiguous bytes) are staged in shared memory and leave as 24 / 6 16-byte stores instead
-    // of 96 4-byte / 1-byte ones — full sectors, which is what peer (NVLink) destinations need
-    // (dist.PeerFrame).
+    // RGB (float32 or 8-bit) into an aligned tile: the warp's 32 pixels — tile_h runs of 32 / tile_h
+    // consecutive pixels — are staged in shared memory and leave as 16-byte (8-byte for 24-byte runs)
+    // vector stores instead of 96 4-byte / 1-byte ones: full sectors, which is what peer (NVLink)
+    // destinations need (dist.PeerFrame).
     __shared__ __align__(16) float stage[LP_TRACE_BLOCK / 32][96];
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     const long long i0 = i - lane;
     const bool vec = (sizeof(T) == 4 || sizeof(T) == 1) && ra.vec_ok && (i0 + 31 < a.n);      // warp-uniform
     RayResult r;
     r.status = 0; r.steps = 0; r.nh = 0; r.fa = 0.0;
-    long long oi = i;
+    int tr = 0, col = 0;
     if (live) {
-        int row, col;
-        tile_pixel(a, cam.width, i, row, col, oi);
+        warp_tile_rc(a, cam.width, i, tr, col);
+        const int row = tile_row(a, tr);
+        const long long pi = (long long)tr * cam.width + col;                    // compact tile index
         const float a32 = (float)pixel_alpha64(cam, cam_x(cam, col), cam_y(cam, row));
         binet_trace<FUSED, FAST, TRIP>(c, L, (double)a32, r);
         if (FUSED && r.steps > a.retrace_steps) binet_trace<false, FAST>(c, L, (double)a32, r);
         const float fa32 = (float)((r.status == 1) ? r.fa : __longlong_as_double(0x7ff8000000000000LL));
         const long long nh = r.nh < 0 ? 0 : (r.nh > 65535 ? 65535 : r.nh);
-        if (a.out_fa) ((float *)a.out_fa)[i] = fa32;
-        if (a.out_w) ((unsigned short *)a.out_w)[i] = (unsigned short)nh;
+        if (a.out_fa) ((float *)a.out_fa)[pi] = fa32;
+        if (a.out_w) ((unsigned short *)a.out_w)[pi] = (unsigned short)nh;
+        const long long oi = a.out_frame_rows ? (long long)(row - a.row0) * cam.width + col : pi;
         T *dst = vec ? (T *)&stage[wrp][0] + lane * 3 : (T *)ra.out + oi * ra.channels;
         remap_pixel<T>(ra, cam, dst, row, col, fa32, (unsigned)nh);
     }
     if (vec) {
-        // vec_ok: the warp's 32 pixels are contiguous in the output (compact tile, or a frame-
-        // addressed tile whose width is a multiple of 32) and start on a 16-byte boundary
+        // vec_ok (host): every run of the warp tile is contiguous in the output and starts on a
+        // vector boundary.  Vector v of the staged 96 floats / bytes belongs to run v / per_run.
         __syncwarp();
-        const long long o0 = __shfl_sync(0xffffffffu, oi, 0);
-        if (lane < (int)(6 * sizeof(T)))
-            reinterpret_cast<uint4 *>((T *)ra.out + o0 * 3)[lane] = reinterpret_cast<const uint4 *>(stage[wrp])[lane];
+        const int th = a.tile_h > 1 ? a.tile_h : 1;
+        const int run_bytes = (32 / th) * 3 * (int)sizeof(T);
+        const int vb = (run_bytes % 16 == 0) ? 16 : 8;
+        const int per_run = run_bytes / vb;
+        const int r0 = __shfl_sync(0xffffffffu, tr, 0), c0 = __shfl_sync(0xffffffffu, col, 0);
+        if (lane < th * per_run) {
+            const int run = lane / per_run, part = lane - run * per_run;
+            const int rr = r0 + run;
+            const long long o0 = a.out_frame_rows ? (long long)(tile_row(a, rr) - a.row0) * cam.width + c0
+                                                  : (long long)rr * cam.width + c0;
+            unsigned char *g = (unsigned char *)((T *)ra.out + o0 * 3) + part * vb;
+            const unsigned char *sm = (const unsigned char *)stage[wrp] + run * run_bytes + part * vb;
+            if (vb == 16) *reinterpret_cast<uint4 *>(g) = *reinterpret_cast<const uint4 *>(sm);
+            else *reinterpret_cast<uint2 *>(g) = *reinterpret_cast<const uint2 *>(sm);
+        }
     }
     if (a.stats) {
         StatAcc acc;
@@ -283,78 +298,6 @@ static long long tile_row_end(int32_t row0, int32_t rows, int32_t band_rows, int
     return (long long)row0 + (r / band_rows) * band_stride + (r % band_rows) + 1;
 }
 
-// ---------------------------------------------------------------------------
-// Schedule selection (one ray per thread vs lane re-packing, lp_repack.cu).
-//
-// Lanes idle in the one-ray-per-thread kernel when the 32 consecutive pixels of a warp need
-// very different numbers of RK4 steps.  That only happens in the annulus around the shadow
-// edge (viewing angle within ~[0.85, 1.45] of alpha_crit: captured rays stop early, rays that
-// graze the photon sphere orbit for a long time) and only if that annulus is NARROW in pixels,
-// so that one warp sees the whole variation.  Estimate of the lost lane fraction:
-//     (tile pixels inside the annulus / tile pixels) * min(1, 32 / annulus width in px)
-// computed exactly over the tile's rows from the projected circle (the BH direction's pinhole
-// projection, radius tan(alpha) * f).  Calibrated on B200 (tools/repack_perf.py).
-// ---------------------------------------------------------------------------
-#define LP_REPACK_LOSS_THRESHOLD 0.05
-
-static double annulus_px_in_rows(const CamConsts &cam, int32_t row0, int32_t rows, int32_t band_rows,
-                                 int32_t band_stride, double cx, double cy, double r_in, double r_out)
-{
-    double area = 0.0;
-    for (int r = 0; r < rows; ++r) {
-        const int row = row0 + (band_rows > 0 ? (r / band_rows) * band_stride + (r % band_rows) : r);
-        const double dy = (double)row + 0.5 - cy;
-        double len = 0.0;
-        const double ho2 = r_out * r_out - dy * dy;
-        if (ho2 > 0.0) {
-            const double ho = sqrt(ho2);
-            const double hi2 = r_in * r_in - dy * dy;
-            const double hi = hi2 > 0.0 ? sqrt(hi2) : 0.0;
-            // two chords [cx-ho, cx-hi] and [cx+hi, cx+ho], clipped to the frame's columns
-            const double segs[2][2] = {{cx - ho, cx - hi}, {cx + hi, cx + ho}};
-            for (int s = 0; s < 2; ++s) {
-                const double lo = segs[s][0] < 0.0 ? 0.0 : segs[s][0];
-                const double hi_c = segs[s][1] > (double)cam.width ? (double)cam.width : segs[s][1];
-                if (hi_c > lo) len += hi_c - lo;
-            }
-        }
-        area += len;
-    }
-    return area;
-}
-
-static int schedule_wants_repack(const CamConsts &cam, int32_t row0, int32_t rows, int32_t band_rows,
-                                 int32_t band_stride, double M, double R_S, double r_obs)
-{
-    if (rows <= 0 || cam.width <= 0) return 0;
-    if (!(cam.d2 > 1e-6) || !(r_obs > 1.5 * R_S)) return 0;      // BH behind / observer inside the photon sphere
-    const double f0 = 1.0 - R_S / r_obs;
-    const double s = 3.0 * sqrt(3.0) * M * sqrt(f0) / r_obs;    // sin(alpha_crit), metrics.py:753-755
-    if (!(s > 0.0) || !(s < 0.95)) return 0;
-    const double ac = asin(s);
-    const double a_in = 0.85 * ac, a_out = 1.45 * ac;
-    if (a_out > 1.2) return 0;
-    const double f = 0.5 * (cam.fx + cam.fy);
-    const double cx = cam.half_w + cam.fx * cam.d0 / cam.d2, cy = cam.half_h + cam.fy * cam.d1 / cam.d2;
-    const double r_in = tan(a_in) * f, r_out = tan(a_out) * f;
-    const double width_px = r_out - r_in;
-    const double area = annulus_px_in_rows(cam, row0, rows, band_rows, band_stride, cx, cy, r_in, r_out);
-    const double frac = area / ((double)rows * cam.width);
-    const double narrow = width_px < 32.0 ? 1.0 : 32.0 / width_px;
-    return frac * narrow > LP_REPACK_LOSS_THRESHOLD ? 1 : 0;
-}
-
-extern "C" int lp_render_schedule(const lp_camera *h_cam, int32_t row0, int32_t rows,
-                                  double M, double R_S, double r_obs, int32_t *repack)
-{
-    CamConsts cam;
-    int rc = lp_make_cam_consts(h_cam, &cam);
-    if (rc != LP_OK) return rc;
-    if (!repack || row0 < 0 || rows < 0 || (long long)row0 + rows > cam.height) return LP_ERR_INVALID_ARG;
-    *repack = schedule_wants_repack(cam, row0, rows, 0, 0, M, R_S, r_obs);
-    return LP_OK;
-}
-
 extern "C" int lp_render_frame_bands(const void *src, int32_t src_dtype, int32_t channels,
                                      const lp_camera *h_cam, int32_t row0, int32_t rows,
                                      int32_t band_rows, int32_t band_stride,
@@ -385,19 +328,27 @@ extern "C" int lp_render_frame_bands(const void *src, int32_t src_dtype, int32_t
     RemapArgs ra;
     ra.src = src; ra.out = out; ra.fa32 = nullptr; ra.w16 = nullptr; ra.n = n;
     ra.row0 = row0; ra.channels = channels; ra.loop_around = render_loop_around; ra.sampling = sampling;
+    // warp tile: LP_RENDER_TILE_H = 1 | 2 | 4 rows per warp (tuning knob; default 4 = 8x4 pixels)
+    static int tile_h_pref = 0;
+    if (!tile_h_pref) {
+        const char *e = getenv("LP_RENDER_TILE_H");
+        const int v = e ? atoi(e) : 0;
+        tile_h_pref = (v == 1 || v == 2 || v == 4) ? v : LP_RENDER_DEFAULT_TILE_H;
+    }
+    int th = tile_h_pref;
+    while (th > 1 && (cam.width % (32 / th) != 0 || rows % th != 0)) th >>= 1;
+    a.tile_h = th; a.tiles_x = cam.width / (32 / th);
     const bool contiguous32 = !a.out_frame_rows || cam.width % 32 == 0;
-    ra.vec_ok = ((flags & LP_RENDER_STAGED_STORES) && channels == 3 && contiguous32 &&
+    const bool runs_ok = th > 1 || contiguous32;        // every run of a warp tile contiguous and vector-aligned
+    ra.vec_ok = ((flags & LP_RENDER_STAGED_STORES) && channels == 3 && runs_ok &&
                  (src_dtype == LP_DTYPE_F32 || src_dtype == LP_DTYPE_U8 || src_dtype == LP_DTYPE_U8_UNIT) &&
                  ((uintptr_t)out % 16) == 0) ? 1 : 0;
     ra.u8_scale = (src_dtype == LP_DTYPE_U8_UNIT) ? 255.0f : 1.0f;
     if (src_dtype == LP_DTYPE_U8_UNIT) src_dtype = LP_DTYPE_U8;
     cudaStream_t st = (cudaStream_t)stream;
-    // schedule: forced by flag, else predicted from the geometry; the re-packing kernel needs the
-    // fast-path precondition (observer strictly inside the integration band)
-    int repack = 0;
-    if (flags & LP_TRACE_REPACK) repack = 1;
-    else if (!(flags & LP_TRACE_NO_REPACK)) repack = schedule_wants_repack(cam, row0, rows, band_rows, band_stride, M, R_S, r_obs);
-    if (repack && lp_binet_fast_ok(&c) && c.valid && n <= 0x7fffffffLL) {
+    // opt-in lane re-packing schedule; it needs the fast-path precondition (observer strictly inside
+    // the integration band), otherwise the request falls through to the default kernel
+    if ((flags & LP_TRACE_REPACK) && lp_binet_fast_ok(&c) && c.valid && n <= 0x7fffffffLL) {
         ra.vec_ok = (contiguous32 && ((uintptr_t)out % 16) == 0) ? 1 : 0;   // chunks are staged by construction
         return lp_launch_render_repack(a, ra, c, cam, src_dtype, flags, st);
     }

@@ -24,7 +24,31 @@ struct TraceArgs {
     // row0 + (r / band_rows) * band_stride + (r % band_rows); band_rows == 0: contiguous
     int32_t band_rows, band_stride;
     int32_t out_frame_rows; // the pixel tile is frame-addressed (LP_RENDER_OUT_FRAME_ROWS)
+    // warp tile of the one-ray-per-thread frame kernel: a warp owns tile_h rows x (32 / tile_h)
+    // columns of pixels instead of 32 consecutive pixels of one row (tile_h = 1).  The RK4 step count
+    // of a ray is a smooth function of its viewing angle, i.e. of the pixel's distance from the black
+    // hole's image, so a compact 8x4 tile has a smaller spread of step counts than a 32x1 strip
+    // (fewer idle lanes around the shadow edge).  tiles_x = width / (32 / tile_h).
+    int32_t tile_h, tiles_x;
 };
+
+// frame row of tile-local row r (interleaved bands, see above)
+__device__ __forceinline__ int tile_row(const TraceArgs &a, int r)
+{
+    if (a.band_rows > 0) r += (r / a.band_rows) * (a.band_stride - a.band_rows);
+    return a.row0 + r;
+}
+
+// thread index -> tile-local (row r, column) under the warp-tile mapping
+__device__ __forceinline__ void warp_tile_rc(const TraceArgs &a, int width, long long i, int &r, int &col)
+{
+    if (a.tile_h <= 1) { pixel_row_col(i, a.n, width, 0, r, col); return; }
+    const unsigned wi = (unsigned)(i >> 5), l = (unsigned)i & 31u;
+    const unsigned tw = 32u / (unsigned)a.tile_h;
+    const unsigned ty = wi / (unsigned)a.tiles_x, tx = wi - ty * (unsigned)a.tiles_x;
+    r = (int)(ty * (unsigned)a.tile_h + l / tw);
+    col = (int)(tx * tw + l % tw);
+}
 
 // tile-local pixel index -> (frame row, column, element index of the pixel in the output tile)
 __device__ __forceinline__ void tile_pixel(const TraceArgs &a, int width, long long i,

@@ -28,8 +28,8 @@ _OUTCOME = {1: "escaped", -1: "captured", 0: "invalid"}
 
 class OdeResult(dict):
     """Attribute-access result bunch with the fields of scipy.integrate.OdeResult that the
-    reference's callers read.  ``sol`` (the dense-output callable) is not materialised: the
-    kernel uses the dense output internally for event location only."""
+    reference's callers read, including ``sol`` — the reference calls
+    ``solve_ivp(..., dense_output=True)`` (geodesic_tracer.py:57-67)."""
 
     def __getattr__(self, name):
         try:
@@ -49,6 +49,40 @@ def _builtin_rhs(metric, base, need_initial_conditions):
             "%s overrides %s: the CUDA generic integrator evaluates %s's own %s on the device and has "
             "no host callback path (no CPU fallback)" % (cls.__name__, ", ".join(changed), base.__name__,
                                                          " / ".join(names)))
+
+
+class DenseSolution:
+    """``OdeResult.sol``: the continuous solution scipy's ``OdeSolution`` of ``RkDenseOutput``
+    segments gives (scipy ivp/common.py OdeSolution, rk.py:715-737), rebuilt from what the kernel
+    recorded per accepted step: ``sol(t) = y_old + h * Q @ (x, x^2, x^3, x^4)``, ``x = (t - t_old)/h``,
+    with Q = K^T P formed on the device.  ``sol(t)`` takes a scalar (-> [8]) or an array (-> [8, n]);
+    like scipy it extrapolates with the first / last segment outside ``[t_min, t_max]``."""
+
+    def __init__(self, ts, ys, hs, Qs):
+        self.ts = np.asarray(ts, dtype=np.float64)           # breakpoints, ascending; the last one is the event time
+        self._y_old = np.asarray(ys, dtype=np.float64)[:, :-1].T.copy()    # [n_seg, 8]
+        self._h = np.asarray(hs, dtype=np.float64)           # [n_seg] full step sizes
+        self._Q = np.asarray(Qs, dtype=np.float64)           # [n_seg, 8, 4]
+        self.n_segments = int(self._h.size)
+        self.t_min, self.t_max = (float(self.ts[0]), float(self.ts[-1])) if self.ts.size else (0.0, 0.0)
+        self.ascending = True
+
+    def _segments(self, t):
+        # OdeSolution: searchsorted(ts, t, side='left') for ascending ts, segment = clip(ind - 1, 0, n - 1)
+        ind = np.searchsorted(self.ts, t, side="left")
+        return np.clip(ind - 1, 0, self.n_segments - 1)
+
+    def __call__(self, t):
+        t = np.asarray(t, dtype=np.float64)
+        scalar = t.ndim == 0
+        tt = np.atleast_1d(t)
+        if self.n_segments == 0:
+            raise ValueError("no integration step was taken: there is nothing to interpolate")
+        seg = self._segments(tt)
+        x = (tt - self.ts[seg]) / self._h[seg]
+        p = np.cumprod(np.stack([x, x, x, x]), axis=0)        # (x, x^2, x^3, x^4)  [4, n]
+        y = np.einsum("nij,jn->in", self._Q[seg], p) * self._h[seg] + self._y_old[seg].T
+        return y[:, 0] if scalar else y
 
 
 def _require_schwarzschild(metric):
@@ -74,7 +108,7 @@ def _alloc(t, n, device):
 
 
 def _paths(metric, alphas=None, state0=None, r_obs=None, lambda_max=1000.0, r_stop_inner=None,
-           r_stop_outer=None, max_points=0):
+           r_stop_outer=None, max_points=0, dense=False):
     """Run the kernel with trajectory recording; grows the trajectory buffer if a ray has
     more accepted points than expected.  Returns host arrays."""
     t = dev.torch()
@@ -92,10 +126,19 @@ def _paths(metric, alphas=None, state0=None, r_obs=None, lambda_max=1000.0, r_st
     d_in = dev.h2d(src.reshape(-1), "rk45_in")
     state, lam, outcome, nsteps, status = _alloc(t, n, d_in.device)
     cap = int(max_points) if max_points else int(min(4096, 2 * lambda_max / MAX_STEP + 64))
+    d_dense = None
     while True:
         traj = t.empty((n, cap, 9), dtype=t.float64, device=d_in.device)
         npts = t.empty(n, dtype=t.int32, device=d_in.device)
-        if state0 is None:
+        if dense:
+            d_dense = t.zeros((n, cap, 25), dtype=t.float64, device=d_in.device)
+            kerr = isinstance(metric, Kerr)
+            e.rk45_paths_dense(1 if kerr else 0, d_in if state0 is None else None, None if state0 is None else d_in,
+                               float(metric.M), float(getattr(metric, "a", 0.0)),
+                               float(metric.r_plus if kerr else metric.R_S), float(0.0 if r_obs is None else r_obs),
+                               float(lambda_max), RTOL, ATOL, MAX_STEP, r_in, r_out, traj, cap, npts, d_dense,
+                               state, lam, outcome, nsteps, status)
+        elif state0 is None:
             e.rk45_trace_paths(d_in, float(metric.M), float(metric.R_S), float(r_obs), float(lambda_max),
                                RTOL, ATOL, MAX_STEP, r_in, r_out, traj, cap, npts, state, lam, outcome,
                                nsteps, status)
@@ -110,14 +153,26 @@ def _paths(metric, alphas=None, state0=None, r_obs=None, lambda_max=1000.0, r_st
         if need <= cap or max_points:
             break
         cap = need
-    return (traj.cpu().numpy(), npts.cpu().numpy(), state.cpu().numpy(), lam.cpu().numpy(),
-            outcome.cpu().numpy(), nsteps.cpu().numpy(), status.cpu().numpy(), r_in, r_out)
+    res = (traj.cpu().numpy(), npts.cpu().numpy(), state.cpu().numpy(), lam.cpu().numpy(),
+           outcome.cpu().numpy(), nsteps.cpu().numpy(), status.cpu().numpy(), r_in, r_out)
+    if dense:
+        return res + (d_dense.cpu().numpy(),)
+    return res
 
 
-def _solution(traj, n_points, state, lam, nsteps, status, r_in, r_out_used):
+def _solution(traj, n_points, state, lam, nsteps, status, r_in, r_out_used, dense=None):
     n = int(n_points)
     ts = traj[:n, 0].copy()
     ys = traj[:n, 1:].T.copy()
+    sol = None
+    if dense is not None:
+        # rows 1 .. n-1 of the kernel's dense buffer: (h, Q[6][4]) over (t, r, theta, phi, p_r, p_theta);
+        # the rows of the two constants of the motion (p_t, p_phi) are zero
+        hs = dense[1:n, 0].copy()
+        Q6 = dense[1:n, 1:].reshape(-1, 6, 4)
+        Q8 = np.zeros((Q6.shape[0], 8, 4))
+        Q8[:, [0, 1, 2, 3, 5, 6]] = Q6
+        sol = DenseSolution(ts, ys, hs, Q8)
     st = int(status)
     t_events = [np.empty(0), np.empty(0)]
     y_events = [np.empty(0), np.empty(0)]
@@ -126,7 +181,7 @@ def _solution(traj, n_points, state, lam, nsteps, status, r_in, r_out_used):
         k = 0 if abs(state[1] - r_in) <= abs(state[1] - r_out_used) else 1
         t_events[k] = np.array([lam])
         y_events[k] = state[None, :].copy()
-    return OdeResult(t=ts, y=ys, sol=None, t_events=t_events, y_events=y_events, nfev=int(nsteps[1]),
+    return OdeResult(t=ts, y=ys, sol=sol, t_events=t_events, y_events=y_events, nfev=int(nsteps[1]),
                      njev=0, nlu=0, status=st, message=_MESSAGES.get(st, ""), success=st >= 0)
 
 
@@ -134,10 +189,10 @@ def integrate_geodesic(metric, state0, lambda_max=1000.0, r_stop_inner=None, r_s
     """Integrate the geodesic equations from an explicit 8-D initial state
     (geodesic_tracer.py:22-71).  Returns ``(solution, 'captured' | 'escaped')``."""
     s0 = np.asarray(state0, dtype=np.float64).reshape(1, 8)
-    traj, npts, state, lam, outcome, nsteps, status, r_in, r_out = _paths(
-        metric, state0=s0, lambda_max=lambda_max, r_stop_inner=r_stop_inner, r_stop_outer=r_stop_outer)
+    traj, npts, state, lam, outcome, nsteps, status, r_in, r_out, dense = _paths(
+        metric, state0=s0, lambda_max=lambda_max, r_stop_inner=r_stop_inner, r_stop_outer=r_stop_outer, dense=True)
     r_out_used = r_out if r_out > 0.0 else float(s0[0, 1]) * 2.0
-    sol = _solution(traj[0], npts[0], state[0], lam[0], nsteps[0], status[0], r_in, r_out_used)
+    sol = _solution(traj[0], npts[0], state[0], lam[0], nsteps[0], status[0], r_in, r_out_used, dense=dense[0])
     return sol, _OUTCOME[int(outcome[0])]
 
 

@@ -332,3 +332,43 @@ def test_hybrid_odd_step_budgets(native, oracle, phi_max, h_max):
         assert rel.max() <= REL_TOL, (flags, rel.max())
         if flags == 0:
             assert (steps.cpu().numpy() != steps_o).mean() < 0.01
+
+
+def test_integration_md_ctypes_stub(native, golden):
+    """INTEGRATION.md section B VERBATIM: the ctypes binding a maintainer of the reference would
+    paste into metrics.py — raw lp_schw_trace_batch_f64 with device pointers, no torch extension in
+    between — against the reference's golden batch (bit for bit except the libm-sine clause rays,
+    which test_batch_golden accounts for; here: classification and winding exact, final_alpha 1e-9)."""
+    import ctypes
+    import os
+    import re
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = re.search(r"```python\n# metrics\.py \(reference\).*?```", text, re.S).group(0)
+    code = block[len("```python\n"):-3]
+    lib_path = os.path.join(root, "light_path_tracer_b200", "_C", "liblightpath.so")
+    code = code.replace("/path/to/light_path_tracer_b200/_C/liblightpath.so", lib_path)
+    # the stub shows the method inside the reference's class body ("..." stands for the rest of it)
+    ns = {"Metric": object}
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
+    m = ns["Schwarzschild"]()
+    g = golden("binet_batch.npz")
+    keys = sorted(k for k in g if k.endswith("_alpha"))
+    assert keys
+    checked = 0
+    for k in keys:
+        tag = k[:-len("_alpha")]
+        m.M = float(g[tag + "_M"])
+        m.R_S = 2.0 * m.M
+        alphas = g[k]
+        out_fa = np.empty(alphas.size, np.float64)
+        out_w = np.empty(alphas.size, np.int64)
+        m.trace_rays_batch(float(g[tag + "_r_obs"]), alphas, out_fa, out_w)
+        ref_fa, ref_w = g[tag + "_fa"], g[tag + "_w"]
+        assert np.array_equal(np.isnan(out_fa), np.isnan(ref_fa)) and np.array_equal(out_w, ref_w)
+        ok = np.isfinite(ref_fa)
+        assert np.all(np.abs(out_fa[ok] - ref_fa[ok]) <= 1e-9 * np.maximum(ref_fa[ok], 1e-3))
+        checked += alphas.size
+    assert checked > 0
+    torch.cuda.synchronize()

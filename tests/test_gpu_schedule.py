@@ -30,7 +30,7 @@ def test_interleaved_bands_equal_full_frame(native, dtype):
         u8 = dtype == "uint8"
         if u8:
             src = (src * 255).to(torch.uint8)
-        full = il.render_frame(src, fov, 30.0, metric, psi=(0.03, -0.02), unit_u8=u8, flags=dev.TRACE_HYBRID | dev.TRACE_NO_REPACK)
+        full = il.render_frame(src, fov, 30.0, metric, psi=(0.03, -0.02), unit_u8=u8, flags=dev.TRACE_HYBRID)
         b = band_layout(H, G, target)
         assert b is not None
         frame = torch.zeros_like(full)
@@ -89,7 +89,7 @@ def test_repack_frame_bit_identical(native, mode):
                     base[..., 0].float().contiguous(), base.contiguous(), (base * 255).to(torch.uint8).contiguous()):
             s0, s1 = dev.new_stats(), dev.new_stats()
             ref, fa0, w0 = il.render_frame(src, fov, r_obs, metric, psi=psi, return_lookups=True, stats=s0,
-                                           flags=flags0 | dev.TRACE_NO_REPACK)
+                                           flags=flags0)
             out, fa1, w1 = il.render_frame(src, fov, r_obs, metric, psi=psi, return_lookups=True, stats=s1,
                                            flags=flags0 | dev.TRACE_REPACK)
             assert torch.equal(ref, out)
@@ -101,28 +101,64 @@ def test_repack_frame_bit_identical(native, mode):
             assert b["sum_warp_steps"] >= b["sum_steps"]
         # row tiles whose pixel count is not a multiple of the chunk
         src = base[..., :3].float().contiguous()
-        ref = il.render_frame(src, fov, r_obs, metric, psi=psi, flags=flags0 | dev.TRACE_NO_REPACK)
+        ref = il.render_frame(src, fov, r_obs, metric, psi=psi, flags=flags0)
         for rows in ((0, 1), (3, H - 5), (H - 1, 1)):
             out = il.render_frame(src, fov, r_obs, metric, psi=psi, rows=rows, flags=flags0 | dev.TRACE_REPACK)
             assert torch.equal(out, ref[rows[0]:rows[0] + rows[1]])
 
 
-def test_repack_1080p_and_schedule_choice(native):
-    """A full 1080p frame through the re-packing kernel equals the default schedule's frame, and
-    the per-launch predictor picks re-packing for the zoomed (divergent) frame only."""
+def test_repack_1080p(native):
+    """A full 1080p frame through the opt-in re-packing kernel equals the default schedule's frame."""
     import torch
-    from light_path_tracer_b200 import _lib
     il, dev, metric, fov = _setup(1080, 1920)
     src = torch.rand(1080, 1920, 3, device="cuda")
-    ref = il.render_frame(src, fov, 100.0, metric, flags=dev.TRACE_HYBRID | dev.TRACE_NO_REPACK)
+    ref = il.render_frame(src, fov, 100.0, metric)
     assert torch.equal(ref, il.render_frame(src, fov, 100.0, metric, flags=dev.TRACE_HYBRID | dev.TRACE_REPACK))
-    assert torch.equal(ref, il.render_frame(src, fov, 100.0, metric))
-    e = _lib.ext()
-    wide = dev.camera_vector((1080, 1920), fov, (0.0, 0.0), il._psi_frame)
-    assert e.render_schedule(wide, 0, 1080, 1.0, 2.0, 100.0) is False
-    il2, _, _, fov2 = _setup(96, 128, 12.0)
-    zoom = dev.camera_vector((96, 128), fov2, (0.0, 0.0), il._psi_frame)
-    assert e.render_schedule(zoom, 0, 96, 1.0, 2.0, 100.0) is True
+
+
+_TILE_SCRIPT = r"""
+import hashlib, sys, numpy as np, torch
+sys.path.insert(0, %r)
+from light_path_tracer_b200 import image_lens as il, _device as dev
+from light_path_tracer_b200.metrics import Schwarzschild
+metric = Schwarzschild(1.0)
+h = hashlib.sha1()
+g = torch.Generator().manual_seed(11)
+for H, W, vdeg, r_obs, psi in ((216, 480, 40.0, 30.0, (0.03, -0.02)), (101, 250, 40.0, 100.0, (0.0, 0.0)),
+                               (96, 128, 12.0, 100.0, (0.0, 0.0)), (64, 72, 20.0, 15.0, (0.1, 0.0))):
+    vfov = np.radians(vdeg)
+    fov = (2 * np.arctan(np.tan(vfov / 2) * W / H), vfov)
+    base = torch.rand(H, W, 3, generator=g)
+    for src in (base.cuda(), (base * 255).to(torch.uint8).cuda()):
+        for fl in (dev.TRACE_HYBRID, dev.TRACE_HYBRID | dev.RENDER_STAGED_STORES, 0):
+            st = dev.new_stats()
+            out, fa, w = il.render_frame(src, fov, r_obs, metric, psi=psi, flags=fl, return_lookups=True, stats=st)
+            s = dev.read_stats(st)
+            h.update(out.cpu().numpy().tobytes()); h.update(fa.cpu().numpy().tobytes()); h.update(w.cpu().numpy().tobytes())
+            h.update(repr((s["n_rays"], s["n_escaped"], s["n_captured"], s["sum_steps"], s["max_steps"])).encode())
+        for rows in ((8, 40), (3, 17)):
+            h.update(il.render_frame(src, fov, r_obs, metric, psi=psi, rows=rows).cpu().numpy().tobytes())
+print(h.hexdigest())
+"""
+
+
+def test_warp_tile_shapes_same_frames(native):
+    """The warp tile of the frame kernel (LP_RENDER_TILE_H = 1: 32x1 strip, 2: 16x2, 4: 8x4 pixels,
+    the default) only changes which lane traces which pixel: frames, lookups and statistics are
+    identical for every shape, with and without staged stores, float32 and 8-bit, full frames and
+    row tiles (odd sizes fall back to narrower tiles)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    digests = {}
+    for th in ("1", "2", "4"):
+        env = dict(os.environ, LP_RENDER_TILE_H=th)
+        res = subprocess.run([sys.executable, "-c", _TILE_SCRIPT % root], env=env, capture_output=True, text=True,
+                             timeout=600)
+        assert res.returncode == 0, res.stderr[-2000:]
+        digests[th] = res.stdout.strip().splitlines()[-1]
+    assert digests["1"] == digests["2"] == digests["4"], digests
 
 
 def test_peer_flags_single_device(native):

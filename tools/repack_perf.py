@@ -38,21 +38,19 @@ def best(fn, k=5):
     return min(ts)
 
 
-print("LP_REPACK_REFILL=%s" % os.environ.get("LP_REPACK_REFILL", "default"))
+print("LP_REPACK_REFILL=%s LP_RENDER_TILE_H=%s" % (os.environ.get("LP_REPACK_REFILL", "default"), os.environ.get("LP_RENDER_TILE_H", "default")))
 for name, H, W, vdeg, r_obs, psi in FRAMES:
     vfov = np.radians(vdeg)
     fov = (2 * np.arctan(np.tan(vfov / 2) * W / H), vfov)
     src = torch.rand(H, W, 3, device="cuda")
     out = torch.empty_like(src)
     res = {}
-    for tag, fl in (("one", dev.TRACE_NO_REPACK), ("repack", dev.TRACE_REPACK)):
+    for tag, fl in (("one", 0), ("repack", dev.TRACE_REPACK)):
         st = dev.new_stats()
         il.render_frame(src, fov, r_obs, metric, psi=psi, out=out, stats=st, flags=dev.TRACE_HYBRID | fl)
         s = dev.read_stats(st)
         ms = best(lambda: il.render_frame(src, fov, r_obs, metric, psi=psi, out=out, flags=dev.TRACE_HYBRID | fl))
         res[tag] = (ms, s["lane_efficiency"], s["sum_steps"] / max(s["n_rays"], 1), s["max_steps"])
-    cam = dev.camera_vector((H, W), fov, psi, il._psi_frame)
-    pick = e.render_schedule(cam, 0, H, 1.0, 2.0, r_obs)
-    print("%-22s one %8.4f ms (lane_eff %.3f)  repack %8.4f ms (lane_eff %.3f)  ratio %.3f  steps/ray %.1f max %d  predictor=%s"
+    print("%-22s one %8.4f ms (lane_eff %.3f)  repack %8.4f ms (lane_eff %.3f)  ratio %.3f  steps/ray %.1f max %d"
           % (name, res["one"][0], res["one"][1], res["repack"][0], res["repack"][1], res["one"][0] / res["repack"][0],
-             res["one"][2], res["one"][3], "repack" if pick else "one"), flush=True)
+             res["one"][2], res["one"][3]), flush=True)
