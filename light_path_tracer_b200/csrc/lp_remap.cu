@@ -33,6 +33,9 @@ lp_remap_kernel(const RemapArgs a, const CamConsts cam)
 // Same per-pixel decisions as remap_pixel(), same integer source index.
 #define LP_REMAP4_BLOCK 128
 #define LP_REMAP4_DEFAULT_QUADS 1
+#define LP_REMAP_DEFAULT_TMA 0
+
+int lp_remap_try_tma(const RemapArgs &a, const CamConsts &cam, int src_dtype, int rows, cudaStream_t stream);
 
 // sin and cos on [0, pi/2] (final_alpha of a sampled pixel is a float32 in that range): one
 // conditional reflection about pi/4 instead of a general quadrant reduction, the fdlibm kernel
@@ -186,6 +189,16 @@ extern "C" int lp_remap(const void *src, int32_t src_dtype, int32_t channels,
     if (a.n == 0) return LP_OK;
     if (!src || !out || !fa32) return LP_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
+    // LP_REMAP_TMA = 1: the TMA-staged kernel (lp_remap_tma.cu) for float32 / uint8 RGB images
+    static int use_tma = -1;
+    if (use_tma < 0) {
+        const char *e = getenv("LP_REMAP_TMA");
+        use_tma = e ? atoi(e) : LP_REMAP_DEFAULT_TMA;
+    }
+    if (use_tma > 0) {
+        const int t = lp_remap_try_tma(a, cam, src_dtype, rows, st);
+        if (t != 0) return t > 0 ? LP_OK : t;
+    }
     if (src_dtype == LP_DTYPE_F32 && channels == 3 && sampling == LP_SAMPLE_NEAREST && cam.width % 4 == 0 &&
         (long long)cam.height * cam.width * 3 < 0x7fffffffLL &&
         ((uintptr_t)out % 16) == 0 && ((uintptr_t)fa32 % 16) == 0 && (!w16 || ((uintptr_t)w16 % 8) == 0)) {

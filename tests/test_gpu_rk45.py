@@ -272,7 +272,7 @@ def test_dense_output_sol_vs_scipy(native):
         assert err.max() <= 1e-10, (type(metric).__name__, r_obs, alpha, err.max(axis=1))
         worst = max(worst, float(err.max()))
         one = sol.sol(float(mids[3]))
-        assert one.shape == (8,) and np.array_equal(one, got[:, ref.t.size + 3])
+        assert one.shape == (8,) and np.allclose(one, got[:, ref.t.size + 3], rtol=1e-14, atol=0.0)
         # the event point is sol(t_event), as solve_ivp builds it (ivp.py:676-697)
         e_evt = np.abs(sol.sol(sol.t[-1]) - sol.y[:, -1]) / np.maximum(np.abs(sol.y[:, -1]), FLOOR)
         assert e_evt.max() <= 1e-12
