@@ -24,9 +24,9 @@
 #define RT_TY 8
 #define RT_NBOX 4
 
-struct TmaBoxes {
-    CUtensorMap map[RT_NBOX];
-};
+// the four tensor maps travel as four separate __grid_constant__ kernel parameters: the TMA unit
+// fetches a descriptor from the address it is given, and only a parameter named directly (not an
+// element of a parameter array picked at run time) is guaranteed to be addressed in place
 // box shapes in (pixels, rows); pixels * 3 elements <= 256 and (pixels * 3 * elem size) % 16 == 0
 // for float32 and uint8 alike
 static const int h_box_px[RT_NBOX] = {48, 64, 80, 80};
@@ -44,7 +44,9 @@ enum { PX_ZERO = 0, PX_WIND = 1, PX_MAGENTA = 2, PX_SAMPLE = 3 };
 
 template <typename T>
 __global__ void __launch_bounds__(RT_TX *RT_TY)
-lp_remap_tma_kernel(const RemapArgs a, const CamConsts cam, const __grid_constant__ TmaBoxes boxes, const int rows)
+lp_remap_tma_kernel(const RemapArgs a, const CamConsts cam, const __grid_constant__ CUtensorMap map0,
+                    const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
+                    const __grid_constant__ CUtensorMap map3, const int rows, const int debug)
 {
     extern __shared__ __align__(128) unsigned char box_smem[];
     __shared__ __align__(8) unsigned long long mbar;
@@ -117,27 +119,39 @@ lp_remap_tma_kernel(const RemapArgs a, const CamConsts cam, const __grid_constan
             by0 = min(by0, red[2][k]); by1 = max(by1, red[3][k]);
         }
         int pick = -1;
+        // the TMA unit faults ("illegal instruction") unless the box starts on a 16-byte boundary of global
+        // memory (tools/tma_probe.cu, profiles/r2g_tma_probe.log): with 3 elements per pixel that is a
+        // multiple of 4 pixels for float32 and of 16 pixels for uint8 (the row pitch is a multiple of 16 bytes)
+        bx0 &= ~((sizeof(T) == 4 ? 4 : 16) - 1);
         if (bx1 >= bx0) {                                    // at least one sampling pixel
             const int need_w = bx1 - bx0 + 1, need_h = by1 - by0 + 1;
 #pragma unroll
             for (int b = RT_NBOX - 1; b >= 0; --b)
                 if (need_w <= c_box_px[b] && need_h <= c_box_rows[b]) pick = b;     // smallest that fits
         }
+        if (debug & 1) pick = -1;
         sel[0] = pick; sel[1] = bx0; sel[2] = by0;
+        if (pick >= 0 && (debug & 4)) pick = -2;      // debug: pretend, issue nothing
         if (pick >= 0) {
             const unsigned bytes = (unsigned)(c_box_px[pick] * 3 * c_box_rows[pick]) * (unsigned)sizeof(T);
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(bytes)
                          : "memory");
-            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
-                         "[%0], [%1, {%2, %3}], [%4];"
-                         ::"r"(smem_u32(box_smem)), "l"((unsigned long long)&boxes.map[pick]), "r"(bx0 * 3), "r"(by0),
-                           "r"(smem_u32(&mbar))
-                         : "memory");
+#define RT_ISSUE(MAP)                                                                                         \
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "                \
+                 "[%0], [%1, {%2, %3}], [%4];"                                                                 \
+                 ::"r"(smem_u32(box_smem)), "l"((unsigned long long)&(MAP)), "r"(bx0 * 3), "r"(by0),         \
+                   "r"(smem_u32(&mbar))                                                                        \
+                 : "memory")
+            if (pick == 0) RT_ISSUE(map0);
+            else if (pick == 1) RT_ISSUE(map1);
+            else if (pick == 2) RT_ISSUE(map2);
+            else RT_ISSUE(map3);
+#undef RT_ISSUE
         }
     }
     __syncthreads();
     const int pick = sel[0];
-    bool staged = pick >= 0;
+    bool staged = pick >= 0 && !(debug & 6);
     if (staged) {
         // wait for the box (phase 0 of the barrier); bounded, so that a TMA that never completes
         // (a bad descriptor) degrades to the global-memory gather instead of hanging the GPU
@@ -215,14 +229,14 @@ int lp_remap_try_tma(const RemapArgs &a, const CamConsts &cam, int src_dtype, in
     if ((long long)cam.width * 3 >= (1ll << 31) || cam.height < 1) return 0;
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return 0;
-    TmaBoxes boxes;
+    CUtensorMap maps[RT_NBOX];
     const cuuint64_t gdim[2] = {(cuuint64_t)cam.width * 3, (cuuint64_t)cam.height};
     const cuuint64_t gstr[1] = {(cuuint64_t)pitch};
     const cuuint32_t estr[2] = {1, 1};
     size_t smem = 0;
     for (int b = 0; b < RT_NBOX; ++b) {
         const cuuint32_t box[2] = {(cuuint32_t)(h_box_px[b] * 3), (cuuint32_t)h_box_rows[b]};
-        const CUresult rc = enc(&boxes.map[b], esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8,
+        const CUresult rc = enc(&maps[b], esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8,
                                 2, const_cast<void *>(a.src), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -230,6 +244,8 @@ int lp_remap_try_tma(const RemapArgs &a, const CamConsts &cam, int src_dtype, in
         const size_t bytes = (size_t)h_box_px[b] * 3 * h_box_rows[b] * esz;
         if (bytes > smem) smem = bytes;
     }
+    const char *de = getenv("LP_REMAP_TMA_DEBUG");
+    const int dbg = de ? atoi(de) : 0;
     const dim3 grid((unsigned)((cam.width + RT_TX - 1) / RT_TX), (unsigned)((rows + RT_TY - 1) / RT_TY));
     if (grid.y > 65535u) return 0;
     if (esz == 4) {
@@ -239,10 +255,10 @@ int lp_remap_try_tma(const RemapArgs &a, const CamConsts &cam, int src_dtype, in
             if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
             attr_f = 1;
         }
-        k<<<grid, RT_TX * RT_TY, smem, stream>>>(a, cam, boxes, rows);
+        k<<<grid, RT_TX * RT_TY, smem, stream>>>(a, cam, maps[0], maps[1], maps[2], maps[3], rows, dbg);
     } else {
         auto k = lp_remap_tma_kernel<unsigned char>;
-        k<<<grid, RT_TX * RT_TY, smem, stream>>>(a, cam, boxes, rows);
+        k<<<grid, RT_TX * RT_TY, smem, stream>>>(a, cam, maps[0], maps[1], maps[2], maps[3], rows, dbg);
     }
     return lp_check_launch() == LP_OK ? 1 : LP_ERR_CUDA;
 }

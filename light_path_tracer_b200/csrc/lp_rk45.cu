@@ -36,6 +36,9 @@
 #define RK_BLOCK 128
 #define RK_REFILL_MIN 8
 #define RK_DEFAULT_MINB 3
+#define RK_DEFAULT_VARIANT 0
+#define RK_DEFAULT_EQ 1
+#define RK_DEFAULT_EQ_MINB 4
 #define RK_NC 6            /* moving components: t, r, theta, phi, p_r, p_theta */
 
 static __constant__ double c_A[6][5] = {
@@ -76,6 +79,7 @@ struct Rk45Args {
     double *dense;              // optional [n][max_points][25]: row k >= 1 = (h, Q[6][4]) of the accepted step
                                 // that ended in point k — scipy's RkDenseOutput (rk.py:178-180, :715-737)
     int32_t refill_min;         // lanes that must be waiting before a flush (RK_REFILL_MIN)
+    int32_t fast_pow;           // step controller: err^-0.2 as exp2(-0.2 log2 err) instead of pow()
 };
 
 struct ThetaCache { double th, s, c; };
@@ -258,10 +262,19 @@ __device__ __forceinline__ void rk_f<1>(const Rk45Args &a, double r_floor, doubl
     rk_rhs_kerr(a.kerr_M, a.kerr_a, r_floor, p_t, p_phi, y, tc, d);
 }
 
-template <int MINB, int METRIC, bool DENSE = false>
-__global__ void __launch_bounds__(RK_BLOCK, MINB)
+// NSM: the stage derivatives K[1] .. K[NSM] live in shared memory ([row][thread], conflict-free
+// 8-byte accesses) instead of registers.  With all seven stage vectors in registers the kernel
+// needs 168+ registers (12 warps per SM) and is bound by the latency of its dependent FP64 chains
+// (ncu round 1: FP64 pipe 52 %, issue 50 %, top stall `wait`); parking the stages that are only
+// read by later stage sums frees ~8 registers per row, and more resident warps hide that latency.
+// Same arithmetic in the same order: results are bit-identical for every NSM.
+template <int MINB, int METRIC, bool DENSE = false, int NSM = 0, int BLOCK = RK_BLOCK>
+__global__ void __launch_bounds__(BLOCK, MINB)
 lp_rk45_kernel(const Rk45Args a)
 {
+    extern __shared__ double rk_ksm_all[];
+    double *const ksm = rk_ksm_all + threadIdx.x;
+#define KGET(j, i) ((((j) >= 1) && ((j) <= NSM)) ? ksm[(((j) - 1) * RK_NC + (i)) * BLOCK] : K[j][i])
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -408,19 +421,26 @@ lp_rk45_kernel(const Rk45Args a)
                 for (int i = 0; i < RK_NC; ++i) {
                     double dy = K[0][i] * c_A[s][0];
 #pragma unroll
-                    for (int j = 1; j < s; ++j) dy = fma(K[j][i], c_A[s][j], dy);
+                    for (int j = 1; j < s; ++j) dy = fma(KGET(j, i), c_A[s][j], dy);
                     ys[i] = fma(dy, h, y[i]);
                 }
-                rk_f<METRIC>(a, r_floor, p_t, p_phi, ys, tc, K[s]);
+                if (s <= NSM) {
+                    double kd[RK_NC];
+                    rk_f<METRIC>(a, r_floor, p_t, p_phi, ys, tc, kd);
+#pragma unroll
+                    for (int i = 0; i < RK_NC; ++i) ksm[((s - 1) * RK_NC + i) * BLOCK] = kd[i];
+                } else {
+                    rk_f<METRIC>(a, r_floor, p_t, p_phi, ys, tc, K[s]);
+                }
             }
             double y_new[RK_NC];
 #pragma unroll
             for (int i = 0; i < RK_NC; ++i) {
                 double acc = K[0][i] * c_B[0];
-                acc = fma(K[2][i], c_B[2], acc);
-                acc = fma(K[3][i], c_B[3], acc);
-                acc = fma(K[4][i], c_B[4], acc);
-                acc = fma(K[5][i], c_B[5], acc);
+                acc = fma(KGET(2, i), c_B[2], acc);
+                acc = fma(KGET(3, i), c_B[3], acc);
+                acc = fma(KGET(4, i), c_B[4], acc);
+                acc = fma(KGET(5, i), c_B[5], acc);
                 y_new[i] = fma(h, acc, y[i]);
             }
             rk_f<METRIC>(a, r_floor, p_t, p_phi, y_new, tc, K[6]);
@@ -433,10 +453,10 @@ lp_rk45_kernel(const Rk45Args a)
             for (int i = 0; i < RK_NC; ++i) {
                 es[i] = atol + fmax(fabs(y[i]), fabs(y_new[i])) * rtol;
                 double acc = K[0][i] * c_E[0];
-                acc = fma(K[2][i], c_E[2], acc);
-                acc = fma(K[3][i], c_E[3], acc);
-                acc = fma(K[4][i], c_E[4], acc);
-                acc = fma(K[5][i], c_E[5], acc);
+                acc = fma(KGET(2, i), c_E[2], acc);
+                acc = fma(KGET(3, i), c_E[3], acc);
+                acc = fma(KGET(4, i), c_E[4], acc);
+                acc = fma(KGET(5, i), c_E[5], acc);
                 acc = fma(K[6][i], c_E[6], acc);
                 en[i] = acc * h;
             }
@@ -456,7 +476,9 @@ lp_rk45_kernel(const Rk45Args a)
             const double error_norm = rms8(esum);
             // one pow for the accept and the reject controller (rk.py:155-170): divergent branches
             // would each run their own copy for the whole warp
-            const double pow_term = 0.9 * pow(error_norm, -0.2);
+            // (fast_pow: x^-0.2 = exp2(-0.2 log2 x), a few ulp — the level at which scipy's own BLAS stage
+            // sums already differ from any restatement; tests hold the accept/reject sequences identical)
+            const double pow_term = 0.9 * (a.fast_pow ? exp2(-0.2 * log2(error_norm)) : pow(error_norm, -0.2));
             if (error_norm < 1) {
                 double factor = (error_norm == 0) ? 10.0 : fmin(10.0, pow_term);
                 if (rejected) factor = fmin(1.0, factor);
@@ -476,7 +498,7 @@ lp_rk45_kernel(const Rk45Args a)
                     for (int m = 0; m < 4; ++m) {
                         double acc = K[0][1] * c_P[0][m];
 #pragma unroll
-                        for (int j = 2; j < 7; ++j) acc = fma(K[j][1], c_P[j][m], acc);
+                        for (int j = 2; j < 7; ++j) acc = fma(KGET(j, 1), c_P[j][m], acc);
                         q[m] = acc;
                     }
                     double root = 0.0;
@@ -495,7 +517,7 @@ lp_rk45_kernel(const Rk45Args a)
                         for (int m = 0; m < 4; ++m) {
                             double acc = K[0][i] * c_P[0][m];
 #pragma unroll
-                            for (int j = 2; j < 7; ++j) acc = fma(K[j][i], c_P[j][m], acc);
+                            for (int j = 2; j < 7; ++j) acc = fma(KGET(j, i), c_P[j][m], acc);
                             qi[m] = acc;
                         }
                         yf[i] = dense_comp(qi, h, y[i], x);
@@ -512,7 +534,7 @@ lp_rk45_kernel(const Rk45Args a)
                         for (int m = 0; m < 4; ++m) {
                             double acc = K[0][i] * c_P[0][m];
 #pragma unroll
-                            for (int j = 2; j < 7; ++j) acc = fma(K[j][i], c_P[j][m], acc);
+                            for (int j = 2; j < 7; ++j) acc = fma(KGET(j, i), c_P[j][m], acc);
                             row[1 + 4 * i + m] = acc;
                         }
                     }
@@ -543,6 +565,332 @@ lp_rk45_kernel(const Rk45Args a)
             active = false;
         }
     }
+#undef KGET
+}
+
+// ---------------------------------------------------------------------------------------------
+// Equatorial specialisation of the batch path (the `alphas` entry: every ray starts from
+// Schwarzschild.initial_conditions, metrics.py:794-809, i.e. theta = pi/2 and p_theta = 0 EXACTLY).
+//
+// In the reference's own integration those two components only carry rounding noise: d theta/d lambda
+// = p_theta / r^2 and d p_theta/d lambda = cos(theta) p_phi^2 / (r^2 sin^3 theta) with cos(pi/2) =
+// 6.1e-17, so |p_theta| stays below ~1e-15 and theta within one ulp of pi/2.  They do not feed back:
+// sin^2(theta) rounds to exactly 1.0 and p_theta^2 + p_phi^2 to p_phi^2, so the right-hand side of the
+// other four components (t, r, phi, p_r) is BIT-IDENTICAL with or without them; their terms of the
+// error norm are ~1e-24 against a sum that is >= 1e-10 whenever the step-size factor is not clamped.
+// This kernel therefore integrates the four live components only (28 stage values instead of 42 in
+// registers, ~2/3 of the FP64 work per step attempt) and reports theta = pi/2, p_theta = 0 — within
+// 3e-16 absolute of what the reference's noise integrates to.  The first-step selection is the full
+// six-component arithmetic (it sees theta / scale = 1e8).  tests/test_gpu_rk45.py holds it to the
+// six-component kernel: same accept/reject sequences, (t, r, phi, p_r) within 1e-12.
+// ---------------------------------------------------------------------------------------------
+#define RK_EQ 4
+
+__device__ __forceinline__ void rk_rhs_eq(double R_S, double r_floor, double p_t, double p_phi, double pp2,
+                                          const double (&y)[RK_EQ], double (&d)[RK_EQ])
+{
+    const double r = y[1], p_r = y[3];
+    if (r <= r_floor) {                                   // metrics.py:766-767
+#pragma unroll
+        for (int i = 0; i < RK_EQ; ++i) d[i] = 0.0;
+        return;
+    }
+    // rk_rhs with sin(theta) = 1, p_theta = 0: the same operations on the same operands
+    const double ir = fast_rcp(r);
+    const double ir2 = ir * ir, ir3 = ir2 * ir;
+    const double f = 1.0 - R_S * ir;
+    const double inv_f = fast_rcp(f);
+    const double a = 0.5 * R_S * ir2;
+    const double ptf = p_t * inv_f;
+    d[0] = -ptf;
+    d[1] = f * p_r;
+    d[2] = p_phi * ir2;
+    d[3] = (-a * (ptf * ptf) - a * (p_r * p_r)) + pp2 * ir3;
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(RK_BLOCK, MINB)
+lp_rk45_eq_kernel(const Rk45Args a)
+{
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const double r_floor = a.r_floor, rtol = a.rtol, atol = a.atol;
+    const double t_bound = a.lambda_max, max_step = a.max_step;
+    const double p_t = -1.0;
+
+    bool active = false, fresh = true, rejected = false;
+    long long idx = -1;
+    double t = 0.0, h_abs = 0.0, p_phi = 0.0, pp2 = 0.0, g0 = 0.0, g1 = 0.0, r_out = 0.0;
+    double y[RK_EQ], f[RK_EQ];                           // (t, r, phi, p_r)
+#pragma unroll
+    for (int i = 0; i < RK_EQ; ++i) { y[i] = 0.0; f[i] = 0.0; }
+    int npts = 0, attempts = 0;
+
+    long long cursor = 0;
+    bool queue_empty = (warp_id * 32 >= a.n);
+
+    while (true) {
+        // ---------------- lane refill (ballot + rank), as lp_rk45_kernel ----------------
+        const unsigned idle = __ballot_sync(full, !active);
+        if (idle && !queue_empty && (__popc(idle) >= a.refill_min || idle == full)) {
+            const int rank = __popc(idle & ((1u << lane) - 1u));
+            const long long v = cursor + rank;
+            const long long ray = ((v >> 5) * n_warps + warp_id) * 32 + (v & 31);
+            cursor += __popc(idle);
+            if (((cursor >> 5) * n_warps + warp_id) * 32 + (cursor & 31) >= a.n) queue_empty = true;
+            if (!active && ray < a.n) {
+                idx = ray;
+                // ---- Schwarzschild.initial_conditions, metrics.py:794-809 ----
+                const double alpha = __ldg(a.alphas + ray);
+                const double b = a.r_obs * lp_sin_cr(alpha) / a.sqrt_f0;
+                const double L = b;
+                const double p_r_sq = (1.0 / a.f0 - (L * L) / (a.r_obs * a.r_obs)) / a.f0;
+                const bool valid = (p_r_sq >= 0.0);
+                if (!valid) {                            // (None, 'invalid'), geodesic_tracer.py:79-81
+                    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+                    for (int k = 0; k < 8; ++k) a.out_state[idx * 8 + k] = qnan;
+                    a.out_lambda[idx] = qnan;
+                    a.out_outcome[idx] = 0;
+                    if (a.out_nsteps) { a.out_nsteps[2 * idx] = 0; a.out_nsteps[2 * idx + 1] = 0; }
+                    if (a.out_status) a.out_status[idx] = -2;
+                } else {
+                    // the six-component state of the reference for the first-step selection
+                    double y6[RK_NC], f6[RK_NC];
+                    y6[0] = 0.0; y6[1] = a.r_obs; y6[2] = LP_PI_D / 2; y6[3] = 0.0;
+                    y6[4] = -__dsqrt_rn(p_r_sq); y6[5] = 0.0;
+                    p_phi = L; pp2 = p_phi * p_phi;
+                    ThetaCache tc;
+                    tc.th = __longlong_as_double(0x7ff8000000000000LL); tc.s = 1.0; tc.c = 0.0;
+                    t = 0.0;
+                    r_out = a.r_out > 0.0 ? a.r_out : y6[1] * 2.0;
+                    rk_rhs(a.R_S, r_floor, p_t, p_phi, y6, tc, f6);                  // rk.py:95
+                    // ---- select_initial_step, common.py:68-134 (direction = +1) ----
+                    const double interval = fabs(t_bound - t);
+                    double sc[RK_NC], d0s = 0.0, d1s = 0.0;
+#pragma unroll
+                    for (int i = 0; i < RK_NC; ++i) {
+                        sc[i] = atol + fabs(y6[i]) * rtol;
+                        const double v0 = y6[i] / sc[i], v1 = f6[i] / sc[i];
+                        d0s = fma(v0, v0, d0s); d1s = fma(v1, v1, d1s);
+                    }
+                    {
+                        const double v4 = p_t / (atol + fabs(p_t) * rtol), v7 = p_phi / (atol + fabs(p_phi) * rtol);
+                        d0s = fma(v4, v4, d0s); d0s = fma(v7, v7, d0s);
+                    }
+                    const double d0 = rms8(d0s), d1 = rms8(d1s);
+                    double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+                    h0 = fmin(h0, interval);
+                    double y1[RK_NC], f1[RK_NC], d2s = 0.0;
+#pragma unroll
+                    for (int i = 0; i < RK_NC; ++i) y1[i] = y6[i] + h0 * f6[i];
+                    rk_rhs(a.R_S, r_floor, p_t, p_phi, y1, tc, f1);
+#pragma unroll
+                    for (int i = 0; i < RK_NC; ++i) { const double v2 = (f1[i] - f6[i]) / sc[i]; d2s = fma(v2, v2, d2s); }
+                    const double d2 = rms8(d2s) / h0;
+                    double h1;
+                    if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
+                    else h1 = pow(0.01 / fmax(d1, d2), 0.2);
+                    h_abs = fmin(fmin(100 * h0, h1), fmin(interval, max_step));
+                    y[0] = y6[0]; y[1] = y6[1]; y[2] = y6[3]; y[3] = y6[4];
+                    f[0] = f6[0]; f[1] = f6[1]; f[2] = f6[3]; f[3] = f6[4];
+                    g0 = y[1] - a.r_in; g1 = y[1] - r_out;                        // ivp.py:650
+                    npts = 1; attempts = 0; fresh = true; rejected = false;
+                    active = (interval != 0.0);
+                    if (!active) {
+                        double *o = a.out_state + idx * 8;
+                        o[0] = y[0]; o[1] = y[1]; o[2] = LP_PI_D / 2; o[3] = y[2]; o[4] = p_t; o[5] = y[3]; o[6] = 0.0; o[7] = p_phi;
+                        a.out_lambda[idx] = t;
+                        a.out_outcome[idx] = (y[1] <= a.r_in * 1.1) ? -1 : 1;
+                        if (a.out_nsteps) { a.out_nsteps[2 * idx] = 1; a.out_nsteps[2 * idx + 1] = 2; }
+                        if (a.out_status) a.out_status[idx] = 0;
+                    }
+                }
+            }
+        }
+        if (!__any_sync(full, active)) {
+            if (queue_empty) break;
+            continue;
+        }
+        if (!active) continue;
+
+        // ---------------- one step attempt (RungeKutta._step_impl, rk.py:111-176) ----------------
+        const double min_step = 10 * fabs((__longlong_as_double(__double_as_longlong(t) + 1LL)) - t);
+        double ha = h_abs;
+        if (fresh) {
+            if (ha > max_step) ha = max_step; else if (ha < min_step) ha = min_step;
+            fresh = false; rejected = false;
+        }
+        int status = 2;
+        double t_fin = t;
+        double yf[RK_EQ];
+#pragma unroll
+        for (int i = 0; i < RK_EQ; ++i) yf[i] = y[i];
+
+        if (ha < min_step) {
+            status = -1;
+        } else {
+            double t_new = t + ha;
+            if (t_new - t_bound > 0) t_new = t_bound;
+            const double h = t_new - t;
+            ha = fabs(h);
+            attempts++;
+            double K[7][RK_EQ];
+#pragma unroll
+            for (int i = 0; i < RK_EQ; ++i) K[0][i] = f[i];
+#pragma unroll
+            for (int s = 1; s < 6; ++s) {
+                double ys[RK_EQ];
+#pragma unroll
+                for (int i = 0; i < RK_EQ; ++i) {
+                    double dy = K[0][i] * c_A[s][0];
+#pragma unroll
+                    for (int j = 1; j < s; ++j) dy = fma(K[j][i], c_A[s][j], dy);
+                    ys[i] = fma(dy, h, y[i]);
+                }
+                rk_rhs_eq(a.R_S, r_floor, p_t, p_phi, pp2, ys, K[s]);
+            }
+            double y_new[RK_EQ];
+#pragma unroll
+            for (int i = 0; i < RK_EQ; ++i) {
+                double acc = K[0][i] * c_B[0];
+                acc = fma(K[2][i], c_B[2], acc);
+                acc = fma(K[3][i], c_B[3], acc);
+                acc = fma(K[4][i], c_B[4], acc);
+                acc = fma(K[5][i], c_B[5], acc);
+                y_new[i] = fma(h, acc, y[i]);
+            }
+            rk_rhs_eq(a.R_S, r_floor, p_t, p_phi, pp2, y_new, K[6]);
+            double esum = 0.0, en[RK_EQ], es[RK_EQ];
+#pragma unroll
+            for (int i = 0; i < RK_EQ; ++i) {
+                es[i] = atol + fmax(fabs(y[i]), fabs(y_new[i])) * rtol;
+                double acc = K[0][i] * c_E[0];
+                acc = fma(K[2][i], c_E[2], acc);
+                acc = fma(K[3][i], c_E[3], acc);
+                acc = fma(K[4][i], c_E[4], acc);
+                acc = fma(K[5][i], c_E[5], acc);
+                acc = fma(K[6][i], c_E[6], acc);
+                en[i] = acc * h;
+            }
+#pragma unroll
+            for (int i = 0; i < RK_EQ; ++i) {
+                const double e = div_by(en[i], es[i], div_rcp(es[i]));
+                esum = fma(e, e, esum);
+            }
+            if (!isfinite(esum)) {
+                esum = 0.0;
+#pragma unroll
+                for (int i = 0; i < RK_EQ; ++i) {
+                    const double e = en[i] / es[i];
+                    esum = fma(e, e, esum);
+                }
+            }
+            const double error_norm = rms8(esum);
+            const double pow_term = 0.9 * (a.fast_pow ? exp2(-0.2 * log2(error_norm)) : pow(error_norm, -0.2));
+            if (error_norm < 1) {
+                double factor = (error_norm == 0) ? 10.0 : fmin(10.0, pow_term);
+                if (rejected) factor = fmin(1.0, factor);
+                ha *= factor;
+                const double gn0 = y_new[1] - a.r_in, gn1 = y_new[1] - r_out;
+                const bool act0 = (g0 >= 0) && (gn0 <= 0);
+                const bool act1 = (g1 <= 0) && (gn1 >= 0);
+                t_fin = t_new;
+#pragma unroll
+                for (int i = 0; i < RK_EQ; ++i) yf[i] = y_new[i];
+                if (t_new - t_bound >= 0) status = 0;
+                if (act0 || act1) {
+                    double q[4];
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        double acc = K[0][1] * c_P[0][m];
+#pragma unroll
+                        for (int j = 2; j < 7; ++j) acc = fma(K[j][1], c_P[j][m], acc);
+                        q[m] = acc;
+                    }
+                    double root = 0.0;
+                    if (act0) root = rk_brentq(q, h, y[1], t, a.r_in, t, t_new);
+                    if (act1) {
+                        const double r1 = rk_brentq(q, h, y[1], t, r_out, t, t_new);
+                        root = (act0 && root <= r1) ? root : r1;
+                    }
+                    status = 1;
+                    t_fin = root;
+                    const double x = (root - t) / h;
+#pragma unroll
+                    for (int i = 0; i < RK_EQ; ++i) {
+                        double qi[4];
+#pragma unroll
+                        for (int m = 0; m < 4; ++m) {
+                            double acc = K[0][i] * c_P[0][m];
+#pragma unroll
+                            for (int j = 2; j < 7; ++j) acc = fma(K[j][i], c_P[j][m], acc);
+                            qi[m] = acc;
+                        }
+                        yf[i] = dense_comp(qi, h, y[i], x);
+                    }
+                }
+                g0 = gn0; g1 = gn1;
+                npts++;
+                t = t_new;
+#pragma unroll
+                for (int i = 0; i < RK_EQ; ++i) { y[i] = y_new[i]; f[i] = K[6][i]; }
+                fresh = true;
+            } else {
+                ha *= fmax(0.2, pow_term);
+                rejected = true;
+            }
+        }
+        h_abs = ha;
+
+        if (status != 2) {
+            double *o = a.out_state + idx * 8;
+            o[0] = yf[0]; o[1] = yf[1]; o[2] = LP_PI_D / 2; o[3] = yf[2];
+            o[4] = p_t; o[5] = yf[3]; o[6] = 0.0; o[7] = p_phi;
+            a.out_lambda[idx] = t_fin;
+            a.out_outcome[idx] = (yf[1] <= a.r_in * 1.1) ? -1 : 1;
+            if (a.out_nsteps) { a.out_nsteps[2 * idx] = npts; a.out_nsteps[2 * idx + 1] = 2 + 6 * attempts; }
+            if (a.out_status) a.out_status[idx] = (int8_t)status;
+            active = false;
+        }
+    }
+}
+
+template <int MINB>
+static int rk45_launch_eq(const Rk45Args &a, cudaStream_t stream)
+{
+    int grid = 0;
+    int rc = lp_grid_for((const void *)lp_rk45_eq_kernel<MINB>, RK_BLOCK, &grid);
+    if (rc != LP_OK) return rc;
+    const long long chunks = (a.n + RK_BLOCK - 1) / RK_BLOCK;
+    if (chunks < grid) grid = (int)chunks;
+    lp_rk45_eq_kernel<MINB><<<grid, RK_BLOCK, 0, stream>>>(a);
+    return lp_check_launch();
+}
+
+template <int MINB, int NSM, int BLOCK>
+static int rk45_launch_variant(const Rk45Args &a, cudaStream_t stream)
+{
+    auto k = lp_rk45_kernel<MINB, 0, false, NSM, BLOCK>;
+    const size_t smem = (size_t)NSM * RK_NC * BLOCK * sizeof(double);
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return LP_ERR_UNSUPPORTED;
+    }
+    if (cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess) cudaGetLastError();
+    int dev = 0, sms = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, BLOCK, smem) != cudaSuccess) {
+        cudaGetLastError();
+        return LP_ERR_CUDA;
+    }
+    long long grid = (long long)sms * (per_sm < 1 ? 1 : per_sm);
+    const long long chunks = (a.n + BLOCK - 1) / BLOCK;
+    if (chunks < grid) grid = chunks;
+    k<<<(unsigned)grid, BLOCK, smem, stream>>>(a);
+    return lp_check_launch();
 }
 
 static int rk45_launch(bool metric_is_kerr, double kerr_a, const double *alphas, const double *state0, int64_t n,
@@ -591,7 +939,52 @@ static int rk45_launch(bool metric_is_kerr, double kerr_a, const double *alphas,
         refill = (v >= 1 && v <= 32) ? v : RK_REFILL_MIN;
     }
     a.refill_min = refill;
+    // LP_RK45_POW = 0 | 1: pow() or exp2(-0.2 log2 x) in the step controller (tuning knob)
+    // default: on in the equatorial batch kernel (4K frame 94 -> 86 ms), off in the six-component kernel of
+    // the single-ray API, whose fixtures were pinned with pow()
+    static int fast_pow = -2;
+    if (fast_pow == -2) {
+        const char *e = getenv("LP_RK45_POW");
+        fast_pow = e ? (atoi(e) != 0) : -1;
+    }
+    a.fast_pow = fast_pow < 0 ? 0 : fast_pow;
     const bool kerr = metric_is_kerr;
+    // LP_RK45_VARIANT (tuning knob, Schwarzschild batch path): how many stage vectors are parked in shared
+    // memory / threads per CTA / resident CTAs per SM (the register cap follows from the last two)
+    static int variant = -1;
+    if (variant < 0) {
+        const char *e = getenv("LP_RK45_VARIANT");
+        variant = e ? atoi(e) : RK_DEFAULT_VARIANT;
+    }
+    // LP_RK45_EQ = 0 | 1: the equatorial four-component kernel for the `alphas` batch entry (no trajectory)
+    static int eq = -1, eq_minb = 0;
+    if (eq < 0) {
+        const char *e = getenv("LP_RK45_EQ");
+        eq = e ? (atoi(e) != 0) : RK_DEFAULT_EQ;
+        const char *m = getenv("LP_RK45_EQ_MINB");
+        const int v = m ? atoi(m) : 0;
+        eq_minb = (v >= 3 && v <= 6) ? v : RK_DEFAULT_EQ_MINB;
+    }
+    if (eq && !kerr && !dense && alphas && !traj && !n_points) {
+        if (fast_pow < 0) a.fast_pow = 1;
+        switch (eq_minb) {
+        case 3: return rk45_launch_eq<3>(a, stream);
+        case 4: return rk45_launch_eq<4>(a, stream);
+        case 5: return rk45_launch_eq<5>(a, stream);
+        default: return rk45_launch_eq<6>(a, stream);
+        }
+    }
+    if (!kerr && !dense && variant > 0) {
+        switch (variant) {
+        case 1: return rk45_launch_variant<8, 4, 64>(a, stream);     // 128 registers, 16 warps / SM
+        case 2: return rk45_launch_variant<7, 3, 64>(a, stream);     // 144 registers, 14 warps / SM
+        case 3: return rk45_launch_variant<4, 4, 128>(a, stream);    // 128 registers, 16 warps / SM
+        case 4: return rk45_launch_variant<9, 5, 64>(a, stream);     // 112 registers, 18 warps / SM
+        case 5: return rk45_launch_variant<6, 0, 64>(a, stream);     // 168 registers, 12 warps / SM, small CTAs
+        case 6: return rk45_launch_variant<10, 5, 64>(a, stream);    // 96 registers, 20 warps / SM
+        default: break;
+        }
+    }
     if (dense) {            // single-ray API (OdeResult.sol): the variant that also stores every step's interpolant
         const void *fd = kerr ? (const void *)lp_rk45_kernel<2, 1, true> : (const void *)lp_rk45_kernel<2, 0, true>;
         int gd = 0;

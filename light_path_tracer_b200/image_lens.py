@@ -133,10 +133,40 @@ def build_alpha_lookup(image_dimension, fov, decimals=None, psi=(0.0, 0.0), *, d
     return out if device else dev.d2h(out, "alpha")
 
 
-def precompute_final_alpha_lookup(alpha_lookup, alpha_crit, r_obs, metric):
+class UniqueAlphaIndex:
+    """The distinct float32 viewing angles of an alpha table and, per pixel, which of them it holds
+    (``np.unique(alpha_lookup, return_inverse=True)``, the idea of the reference's older driver,
+    debugging_image_lense.py:634-640).  It depends on the camera only, so a sweep over observer
+    distances builds it once: ``idx = UniqueAlphaIndex(alpha_lookup)`` and then
+    ``precompute_final_alpha_lookup(alpha_lookup, ac, r_obs, metric, unique=idx)`` per frame."""
+
+    def __init__(self, alpha_lookup):
+        t = dev.torch()
+        a32 = alpha_lookup if _is_tensor(alpha_lookup) else dev.h2d(np.asarray(alpha_lookup, dtype=np.float32), "alpha")
+        if a32.dtype != t.float32:
+            raise TypeError("UniqueAlphaIndex takes the float32 alpha table")
+        self.shape = tuple(a32.shape)
+        # bit patterns, so that -0.0 / 0.0 and NaN payloads stay distinct rays like in the per-pixel path
+        bits = a32.contiguous().view(t.int32).reshape(-1)
+        u, inv = t.unique(bits, sorted=True, return_inverse=True)
+        self.alpha = u.view(t.float32)
+        self.inverse = inv
+        self.n_unique = int(u.numel())
+
+
+def precompute_final_alpha_lookup(alpha_lookup, alpha_crit, r_obs, metric, *, unique=False):
     """One ray per pixel (image_lens.py:155-178) -> (final_alpha float32[H,W],
     winding uint16[H,W], total_rays, traced_rays).  ``alpha_crit`` is unused, as in the
     reference: shadow pixels are integrated too.
+
+    ``unique=True`` (or a ``UniqueAlphaIndex``; opt-in, Schwarzschild only): for a spherically
+    symmetric metric final_alpha and the winding number are functions of the viewing angle alone,
+    so every DISTINCT float32 alpha is traced once and the result is scattered back to the pixels
+    that hold it.  No interpolation: the lookups are bit-identical to the per-pixel path (pixel
+    symmetry alone makes most alphas of an on-axis frame occur 4-8 times; with
+    ``build_alpha_lookup(decimals=...)`` bins, thousands of times); ``traced_rays`` reports the
+    number of distinct angles.  Off by default because finding the distinct values (a device sort)
+    costs about as much as tracing a 4K frame; it pays when the index is reused across frames.
 
     A ``Schwarzschild`` metric takes the single-launch GPU path on the float32 table; any
     other ``Metric`` goes through its own ``trace_rays_batch`` in 50 000-ray chunks
@@ -154,6 +184,18 @@ def precompute_final_alpha_lookup(alpha_lookup, alpha_crit, r_obs, metric):
     if isinstance(metric, Schwarzschild) and type(metric).trace_rays_batch is Schwarzschild.trace_rays_batch:
         t = dev.torch()
         is_f32 = (alpha_lookup.dtype == t.float32) if tensor_in else (np.asarray(alpha_lookup).dtype == np.float32)
+        if unique is not False and unique is not None:
+            if not is_f32:
+                raise TypeError("unique-alpha tracing works on the float32 alpha table")
+            index = unique if isinstance(unique, UniqueAlphaIndex) else UniqueAlphaIndex(alpha_lookup)
+            if index.shape != shape:
+                raise ValueError("UniqueAlphaIndex was built for a table of shape %r" % (index.shape,))
+            fa_u, w_u = metric.trace_alpha_table(index.alpha, r_obs)
+            fa = fa_u[index.inverse].reshape(shape)
+            w = w_u.view(t.int16)[index.inverse].view(t.uint16).reshape(shape)
+            if tensor_in:
+                return fa, w, n, index.n_unique
+            return dev.d2h(fa, "fa32"), dev.d2h(w, "w16"), n, index.n_unique
         if is_f32:
             a32 = alpha_lookup.contiguous() if tensor_in else dev.h2d(np.asarray(alpha_lookup), "alpha")
             fa, w = metric.trace_alpha_table(a32, r_obs)

@@ -77,3 +77,30 @@ def rel_err(a, b, floor=0.0):
     if not m.any():
         return 0.0
     return float(np.max(np.abs(a[m] - b[m]) / np.maximum(np.abs(b[m]), floor if floor else 1e-300)))
+
+
+_PARITY_COUNTS = {}
+
+
+def record_parity(key, **counts):
+    """Per-configuration parity counts (rays that needed a documented clause, pixels that differ and
+    why): collected over the session and written to gpurun_out/parity_counts.json (or
+    $LP_PARITY_REPORT) so that a regression in a COUNT is visible, not only a crossed bound."""
+    _PARITY_COUNTS[key] = {k: (int(v) if isinstance(v, (bool, int, np.integer)) else float(v)) for k, v in counts.items()}
+
+
+def pytest_sessionfinish(session, exitstatus):
+    if not _PARITY_COUNTS:
+        return
+    path = os.environ.get("LP_PARITY_REPORT") or os.path.join(ROOT, "gpurun_out", "parity_counts.json")
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        old = {}
+        if os.path.exists(path):
+            with open(path) as f:
+                old = json.load(f)
+        old.update(_PARITY_COUNTS)
+        with open(path, "w") as f:
+            json.dump(old, f, indent=1, sort_keys=True)
+    except OSError:
+        pass

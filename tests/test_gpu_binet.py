@@ -75,6 +75,9 @@ def _check_batch(M, r_obs, alpha, fa_ref, w_ref, fa, w, what, oracle=None):
         assert n_sens <= max(3, 0.01 * alpha.size), "%s: %d rays needed the libm-sensitivity clause" % (what, n_sens)
     clean = same & ~suspect
     worst = float(err[clean].max()) if clean.any() else 0.0
+    from conftest import record_parity
+    record_parity("binet/" + what, rays=alpha.size, libm_sine_clause_rays=n_sens,
+                  flips_within_1e9_of_b_crit=int((flips & in_band).sum()), worst_rel_err_of_the_rest=worst)
     return int((flips & in_band).sum()) + n_sens, worst
 
 
