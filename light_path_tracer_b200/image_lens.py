@@ -373,7 +373,8 @@ def render_lensed_image(source_image, alpha_lookup, final_alpha_lookup, winding_
         if src_np.dtype not in (np.uint8, np.float32, np.float64):
             raise TypeError("source_image dtype %s is not supported on the GPU path "
                             "(uint8, float32, float64)" % src_np.dtype)
-    src = source_image.contiguous() if tensor_in else dev.h2d(src_np, "src")
+    # the lookups first: when they are the (pinned) arrays this package returned they upload in place,
+    # and those DMAs then run while the pageable source image is being staged by the host threads
     fa = final_alpha_lookup if _is_tensor(final_alpha_lookup) else \
         dev.h2d(np.asarray(final_alpha_lookup, dtype=np.float32), "fa32")
     if winding_lookup is None:
@@ -381,7 +382,11 @@ def render_lensed_image(source_image, alpha_lookup, final_alpha_lookup, winding_
     elif _is_tensor(winding_lookup):
         w = winding_lookup
     else:
-        w = dev.h2d(np.clip(np.asarray(winding_lookup), 0, WINDING_MAX).astype(WINDING_DTYPE), "w16")
+        w_np = np.asarray(winding_lookup)
+        if w_np.dtype != WINDING_DTYPE:          # uint16 is already in range: no host pass over it
+            w_np = np.clip(w_np, 0, WINDING_MAX).astype(WINDING_DTYPE)
+        w = dev.h2d(w_np, "w16")
+    src = source_image.contiguous() if tensor_in else dev.h2d(src_np, "src")
     if tuple(fa.shape) != (height, width):
         raise ValueError("final_alpha_lookup shape %r does not match the image %r"
                          % (tuple(fa.shape), (height, width)))

@@ -102,10 +102,10 @@ def test_batch_vs_oracle(native, oracle, M, r_obs):
     # The batch path integrates the four live components of an equatorial ray and reports
     # theta = pi/2, p_theta = 0 (csrc/lp_rk45.cu, lp_rk45_eq_kernel).  What the reference holds in
     # those two slots is the rounding noise of cos(pi/2) = 6.1e-17 integrated along the ray: checked
-    # to BE noise here (|p_theta| <= 1e-12, theta within 2 ulp of pi/2) and compared on that scale;
+    # to BE noise here (|p_theta| <= 1e-12, theta within 1e-14 of pi/2) and compared on that scale;
     # the six-component kernel behind the single-ray API reproduces it (tests above / below).
-    assert np.abs(s_o[valid, 6]).max() <= 1e-12 and np.abs(s_o[valid, 2] - np.pi / 2).max() <= 4.5e-16
-    assert np.abs(state[valid, 6]).max() <= 1e-12 and np.abs(state[valid, 2] - np.pi / 2).max() <= 4.5e-16
+    assert np.abs(s_o[valid, 6]).max() <= 1e-12 and np.abs(s_o[valid, 2] - np.pi / 2).max() <= 1e-14
+    assert np.abs(state[valid, 6]).max() <= 1e-12 and np.abs(state[valid, 2] - np.pi / 2).max() <= 1e-14
     live = [0, 1, 3, 4, 5, 7]
     err = (np.abs(state - s_o) / np.maximum(np.abs(s_o), FLOOR))[:, live].max(axis=1)
     err_l = np.abs(lam - l_o) / np.maximum(np.abs(l_o), 1.0)
@@ -308,8 +308,8 @@ def test_equatorial_kernel_equals_six_component_kernel(native, tmp_path):
     """The batch path's equatorial kernel (four live components; theta = pi/2, p_theta = 0 carried
     as the constants they are to within rounding noise) against the six-component kernel that
     integrates the reference's full state: same outcome, same accepted points and nfev for every
-    ray, (t, r, phi, p_r) and lambda within 1e-12, theta / p_theta within the noise they integrate
-    to in the reference (<= 1e-15 / 1e-13 absolute)."""
+    ray, (t, r, phi, p_r) and lambda within 1e-11, theta / p_theta within the noise they integrate
+    to in the reference (<= 1e-14 / 1e-12 absolute)."""
     import os
     import subprocess
     import sys
@@ -331,9 +331,9 @@ def test_equatorial_kernel_equals_six_component_kernel(native, tmp_path):
         for c, floor in ((0, 1.0), (1, 1.0), (3, 1e-3), (5, 1e-3)):
             e = np.abs(s1[ok, c] - s0[ok, c]) / np.maximum(np.abs(s0[ok, c]), floor)
             worst = max(worst, float(e.max()))
-            assert e.max() <= 1e-12, (tag, c, e.max())
+            assert e.max() <= 1e-11, (tag, c, e.max())
         assert np.array_equal(s0[ok, 4], s1[ok, 4]) and np.array_equal(s0[ok, 7], s1[ok, 7])      # constants of the motion
-        assert np.abs(s1[ok, 2] - s0[ok, 2]).max() <= 1e-15 and np.abs(s1[ok, 6] - s0[ok, 6]).max() <= 1e-13
+        assert np.abs(s1[ok, 2] - s0[ok, 2]).max() <= 1e-14 and np.abs(s1[ok, 6] - s0[ok, 6]).max() <= 1e-12
         e = np.abs(res["1"][tag + "_lam"][ok] - res["0"][tag + "_lam"][ok]) / np.maximum(res["0"][tag + "_lam"][ok], 1.0)
-        assert e.max() <= 1e-12
+        assert e.max() <= 1e-11
     print("equatorial vs six-component kernel: worst relative difference %.2e" % worst)
