@@ -281,6 +281,8 @@ def run_gpu(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    # one process per GPU: run on (and take pinned host memory from) the GPU's own NUMA node
+    numa_node = dev.bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     ext = _lib.ext()
@@ -488,6 +490,11 @@ def run_gpu(args):
                             ("dist.ShardedHostFrames: every frame is a NEW pinned uint8 source — every rank uploads "
                              "its 1/N of the rows, NCCL all-gather replicates it over NVLink, lp_render_frame renders "
                              "the rank's rows, D2H of the rows to pinned memory; 3 slots on 3 streams")},
+            "host": {"numa_node_of_rank0": numa_node, "cpus_rank0": len(os.sched_getaffinity(0)),
+                     "e2e_host_bytes_per_s": rays * 6 * args.steps / (total_e2e * 1e-3),
+                     "note": "every rank is pinned to its GPU's NUMA node before it allocates pinned memory "
+                             "(_device.bind_to_gpu_numa_node); e2e_host_bytes_per_s = host->device + device->host "
+                             "bytes of all ranks per second of the e2e leg"},
             "gpu_launches": args.steps * launches_per_step,
             "gather": gather_mode,
             "roofline": fp64_roofline("lp_render_kernel (alpha + Binet RK4 + remap, fused)", flops_max_tile, kern_ms,

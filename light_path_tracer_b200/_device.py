@@ -51,6 +51,39 @@ def device():
     return t.device("cuda", t.cuda.current_device())
 
 
+def bind_to_gpu_numa_node(index=None):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (one process per GPU): pinned
+    staging memory allocated afterwards is then local to the GPU's PCIe root port instead of
+    wherever the launcher started the process — on a two-socket host, remote pinned memory halves
+    the aggregate host<->device bandwidth of an 8-GPU job.  Best effort: returns the node (or None
+    when the topology is not visible, e.g. in a restricted container) and never raises."""
+    try:
+        t = torch()
+        index = t.cuda.current_device() if index is None else int(index)
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        path = "/sys/bus/pci/devices/%s:%s/numa_node" % (dom[-4:].lower(), rest.lower())
+        with open(path) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def _copy_pool():
     global _pool
     if _pool is None:

@@ -184,6 +184,8 @@ extern "C" int lp_remap(const void *src, int32_t src_dtype, int32_t channels,
     a.n = (long long)rows * cam.width;
     a.row0 = row0; a.channels = channels; a.loop_around = render_loop_around; a.sampling = sampling;
     a.vec_ok = 0;
+    a.fast3 = (channels == 3 && sampling == LP_SAMPLE_NEAREST &&
+               (long long)cam.height * cam.width * 3 < 0x7fffffffLL) ? 1 : 0;
     a.u8_scale = (src_dtype == LP_DTYPE_U8_UNIT) ? 255.0f : 1.0f;
     if (src_dtype == LP_DTYPE_U8_UNIT) src_dtype = LP_DTYPE_U8;
     if (a.n == 0) return LP_OK;

@@ -36,6 +36,7 @@ struct RemapArgs {
     int32_t sampling;
     int32_t vec_ok;              // fused kernel: float32 RGB into a 16-byte aligned tile
     float u8_scale;              // 255 for LP_DTYPE_U8_UNIT images, else 1
+    int32_t fast3;               // RGB, nearest sampling, H*W*3 < 2^31: 32-bit index arithmetic
 };
 
 // python `a % n` for n > 0
@@ -98,6 +99,39 @@ __device__ __forceinline__ void remap_pixel(const RemapArgs &a, const CamConsts 
 {   // dst: where this pixel's `channels` values go (global memory, or a staging slot)
     const int C = a.channels;
     const T *__restrict__ src = (const T *)a.src;
+    if (a.fast3) {
+        // the common layout — three channels, nearest sampling, an image whose element count fits
+        // 31 bits — with the decisions of the general code below on 32-bit integers:
+        // cvt.rni.s32.f64 rounds half to even like np.rint and saturates, so a far out-of-frame
+        // coordinate stays out of frame (same as lp_remap_f32rgb_x4_kernel, pixel-identical)
+        if (!isfinite(fa32)) { dst[0] = (T)0; dst[1] = (T)0; dst[2] = (T)0; return; }
+        if (fa32 > LP_HALF_PI_F32) {
+            const unsigned k = wnd > 4u ? 4u : wnd;
+            dst[0] = colour<T>(c_wind_rgb[k][0], a.u8_scale); dst[1] = colour<T>(c_wind_rgb[k][1], a.u8_scale);
+            dst[2] = colour<T>(c_wind_rgb[k][2], a.u8_scale);
+            return;
+        }
+        double px, py;
+        const bool front = source_coords(cam, row, col, fa32, px, py);
+        const int H = cam.height, W = cam.width;
+        int ix = __double2int_rn(px), iy = __double2int_rn(py);
+        bool ok;
+        if (a.loop_around) {
+            ix %= W; ix += (ix < 0) ? W : 0;
+            iy %= H; iy += (iy < 0) ? H : 0;
+            ok = true;
+        } else {
+            ok = front && (unsigned)ix < (unsigned)W && (unsigned)iy < (unsigned)H;
+        }
+        if (!ok) {
+            const T one = colour<T>(1.0f, a.u8_scale);
+            dst[0] = one; dst[1] = (T)0; dst[2] = one;
+            return;
+        }
+        const T *s = src + (iy * W + ix) * 3;
+        dst[0] = __ldg(s); dst[1] = __ldg(s + 1); dst[2] = __ldg(s + 2);
+        return;
+    }
     if (!isfinite(fa32)) {                                   // captured / invalid: zeros_like
         for (int ch = 0; ch < C; ++ch) dst[ch] = (T)0;
         return;

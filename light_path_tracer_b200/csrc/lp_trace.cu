@@ -344,6 +344,8 @@ extern "C" int lp_render_frame_bands(const void *src, int32_t src_dtype, int32_t
                  (src_dtype == LP_DTYPE_F32 || src_dtype == LP_DTYPE_U8 || src_dtype == LP_DTYPE_U8_UNIT) &&
                  ((uintptr_t)out % 16) == 0) ? 1 : 0;
     ra.u8_scale = (src_dtype == LP_DTYPE_U8_UNIT) ? 255.0f : 1.0f;
+    ra.fast3 = (channels == 3 && sampling == LP_SAMPLE_NEAREST &&
+                (long long)cam.height * cam.width * 3 < 0x7fffffffLL) ? 1 : 0;
     if (src_dtype == LP_DTYPE_U8_UNIT) src_dtype = LP_DTYPE_U8;
     cudaStream_t st = (cudaStream_t)stream;
     // opt-in lane re-packing schedule; it needs the fast-path precondition (observer strictly inside

@@ -1,6 +1,7 @@
 """One small, fixed workload per case for ncu captures (gpurun: plain run first, then under ncu).
 
-    python tools/ncu_case.py render_hybrid | render_strict | trace_hybrid | remap | rk45 | shadow
+    python tools/ncu_case.py render_hybrid | render_u8 | render_strict | trace_hybrid | remap | remap_tma | rk45 | rk45_full | kerr | shadow
+(remap_tma and rk45_full set LP_REMAP_TMA=1 / LP_RK45_EQ=0 for their process)
 """
 import os
 import sys
@@ -13,6 +14,10 @@ from light_path_tracer_b200 import image_lens as il, geodesic_tracer as gt, blac
 from light_path_tracer_b200.metrics import Schwarzschild  # noqa: E402
 
 case = sys.argv[1]
+if case == "remap_tma":
+    os.environ["LP_REMAP_TMA"] = "1"
+if case == "rk45_full":
+    os.environ["LP_RK45_EQ"] = "0"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 H, W = 2160, 3840
 vfov = np.radians(40.0)
@@ -22,16 +27,18 @@ src = torch.rand(H, W, 3, device="cuda")
 for _ in range(reps):
     if case == "render_hybrid":
         il.render_frame(src, fov, 100.0, m, flags=4)
+    elif case == "render_u8":
+        il.render_frame((src * 255).to(torch.uint8), fov, 100.0, m, flags=4 | 8, unit_u8=True)
     elif case == "render_strict":
         il.render_frame(src, fov, 100.0, m, flags=0)
     elif case == "trace_hybrid":
         a = il.build_alpha_lookup((H, W), fov, device=True)
         m.trace_alpha_table(a, 100.0, flags=4)
-    elif case == "remap":
+    elif case in ("remap", "remap_tma"):
         a = il.build_alpha_lookup((H, W), fov, device=True)
         fa, w = m.trace_alpha_table(a, 100.0)
         il.render_lensed_image(src, a, fa, w, 0.0, fov)
-    elif case == "rk45":
+    elif case in ("rk45", "rk45_full"):
         h, w_ = 540, 960
         f2 = (2 * np.arctan(np.tan(vfov / 2) * w_ / h), vfov)
         a = il.build_alpha_lookup((h, w_), f2, device=True).double()
