@@ -93,9 +93,10 @@ __device__ __forceinline__ bool source_coords(const CamConsts &cam, int row, int
     return source_coords_xy(cam, cam_x(cam, col), cam_y(cam, row), fa32, px, py);
 }
 
+// xc, yc: the pixel's camera-plane coordinates cam_x(col), cam_y(row)
 template <typename T>
-__device__ __forceinline__ void remap_pixel(const RemapArgs &a, const CamConsts &cam, T *__restrict__ dst,
-                                            int row, int col, float fa32, unsigned wnd)
+__device__ __forceinline__ void remap_pixel_xy(const RemapArgs &a, const CamConsts &cam, T *__restrict__ dst,
+                                               double xc, double yc, float fa32, unsigned wnd)
 {   // dst: where this pixel's `channels` values go (global memory, or a staging slot)
     const int C = a.channels;
     const T *__restrict__ src = (const T *)a.src;
@@ -112,7 +113,7 @@ __device__ __forceinline__ void remap_pixel(const RemapArgs &a, const CamConsts 
             return;
         }
         double px, py;
-        const bool front = source_coords(cam, row, col, fa32, px, py);
+        const bool front = source_coords_xy(cam, xc, yc, fa32, px, py);
         const int H = cam.height, W = cam.width;
         int ix = __double2int_rn(px), iy = __double2int_rn(py);
         bool ok;
@@ -146,7 +147,7 @@ __device__ __forceinline__ void remap_pixel(const RemapArgs &a, const CamConsts 
         return;
     }
     double px, py;
-    const bool front = source_coords(cam, row, col, fa32, px, py);
+    const bool front = source_coords_xy(cam, xc, yc, fa32, px, py);
     const long long H = cam.height, W = cam.width;
     long long ix = (long long)rint(px), iy = (long long)rint(py);   // np.rint -> intp
     bool ok;
@@ -190,3 +191,9 @@ __device__ __forceinline__ void remap_pixel(const RemapArgs &a, const CamConsts 
     }
 }
 
+template <typename T>
+__device__ __forceinline__ void remap_pixel(const RemapArgs &a, const CamConsts &cam, T *__restrict__ dst,
+                                            int row, int col, float fa32, unsigned wnd)
+{
+    remap_pixel_xy<T>(a, cam, dst, cam_x(cam, col), cam_y(cam, row), fa32, wnd);
+}

@@ -30,6 +30,12 @@ struct TraceArgs {
     // hole's image, so a compact 8x4 tile has a smaller spread of step counts than a 32x1 strip
     // (fewer idle lanes around the shadow edge).  tiles_x = width / (32 / tile_h).
     int32_t tile_h, tiles_x;
+    // tile_shift = log2(tile_h); tiles_x_magic = ceil(2^32 / tiles_x) when the host has verified that
+    // __umulhi(w, magic) == w / tiles_x for every warp tile index w of this launch, else 0 (plain division)
+    uint32_t tile_shift, tiles_x_magic;
+    // frame kernel, ticket schedule (lp_trace.cu): tickets in this launch (0 = static one tile per warp),
+    // warp tiles per ticket, counter slot
+    int32_t dyn_tickets, dyn_span, dyn_slot;
 };
 
 // frame row of tile-local row r (interleaved bands, see above)
@@ -44,10 +50,11 @@ __device__ __forceinline__ void warp_tile_rc(const TraceArgs &a, int width, long
 {
     if (a.tile_h <= 1) { pixel_row_col(i, a.n, width, 0, r, col); return; }
     const unsigned wi = (unsigned)(i >> 5), l = (unsigned)i & 31u;
-    const unsigned tw = 32u / (unsigned)a.tile_h;
-    const unsigned ty = wi / (unsigned)a.tiles_x, tx = wi - ty * (unsigned)a.tiles_x;
-    r = (int)(ty * (unsigned)a.tile_h + l / tw);
-    col = (int)(tx * tw + l % tw);
+    const unsigned tw_shift = 5u - a.tile_shift;
+    const unsigned ty = a.tiles_x_magic ? __umulhi(wi, a.tiles_x_magic) : wi / (unsigned)a.tiles_x;
+    const unsigned tx = wi - ty * (unsigned)a.tiles_x;
+    r = (int)((ty << a.tile_shift) + (l >> tw_shift));
+    col = (int)((tx << tw_shift) + (l & ((1u << tw_shift) - 1u)));
 }
 
 // tile-local pixel index -> (frame row, column, element index of the pixel in the output tile)

@@ -84,7 +84,7 @@ static void run(int wps, int trips, double *d_out)
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
         if (rep && ms < best) best = ms;
     }
-    const double fp64_inst = (double)grid * 4.0 * trips * 4.0 * 22.0 * ILP;   // warp instructions
+    const double fp64_inst = (double)grid * 4.0 * trips * 4.0 * 18.0 * ILP;   // warp instructions
     const double cycles = best * 1e-3 * 1.965e9;
     printf("ILP %d  warps/SMSP %2d (occ %2d)  trips %d  %.3f ms  FP64 pipe utilisation %.3f\n", ILP, wps, occ, trips, best,
            fp64_inst * 2.0 / (cycles * 592.0));
