@@ -58,6 +58,16 @@ int lp_grid_for(const void *kernel, int block, int *grid_out)
 // metrics.py:51-78 evaluated once per configuration instead of once per ray.  Every
 // expression keeps the reference's operation order; this translation unit is compiled
 // with host FMA contraction disabled.
+// x / d == div_by(x, d, RN(1/d)) (lp_internal.cuh) for every x whose quotient is normal: d normal and far
+// from the exponent limits, significand not all ones (the one case Markstein's theorem excludes).
+static int div_const_exact(double d)
+{
+    if (!(d > 1e-100) || !(d < 1e100)) return 0;
+    unsigned long long bits;
+    memcpy(&bits, &d, 8);
+    return (bits & 0xfffffffffffffull) != 0xfffffffffffffull;
+}
+
 int lp_make_binet_consts(double M, double R_S, double r_obs, double phi_max, double h_max,
                          BinetConsts *c)
 {
@@ -80,6 +90,9 @@ int lp_make_binet_consts(double M, double R_S, double r_obs, double phi_max, dou
     c->cap_r = R_S * 1.1;
     c->r_esc = 1.0 / c->ue;
     c->ue_sq = c->ue * c->ue;
+    c->inv_sqrt_f0 = 1.0 / c->sqrt_f0;
+    c->inv_ue_sq = 1.0 / c->ue_sq;
+    c->div_const_ok = div_const_exact(c->sqrt_f0) && div_const_exact(c->ue_sq);
 
     // replay the phi bookkeeping of the while-loop (metrics.py:72-78, :93, :115)
     int shift = 0;

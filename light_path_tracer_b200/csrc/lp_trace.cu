@@ -234,7 +234,7 @@ static __device__ __forceinline__ void lp_stats_flush_warp(const StatAcc &a, uns
     }
 }
 
-template <bool FUSED, bool FAST, typename T, int MINB, int TRIP>
+template <bool FUSED, bool FAST, typename T, int MINB, int TRIP, bool DYN = false>
 __global__ void __launch_bounds__(LP_TRACE_BLOCK, MINB)
 lp_render_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts c, const CamConsts cam)
 {
@@ -245,7 +245,7 @@ lp_render_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts c, con
     // destinations need (dist.PeerFrame).
     __shared__ __align__(16) float stage[LP_TRACE_BLOCK / 32][96];
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-    const bool dyn = a.dyn_tickets > 0;
+    const bool dyn = DYN;
     unsigned int *const tickets = g_lp_tickets + a.dyn_slot * LP_TICKET_STRIDE;
     const unsigned int n_warps = gridDim.x * (blockDim.x >> 5);
     unsigned int cur = 0, nxt = 0;       // current ticket (warp-uniform); the next one (lane 0, requested early)
@@ -284,8 +284,10 @@ lp_render_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts c, con
             if (a.out_fa) ((float *)a.out_fa)[pi] = fa32;
             if (a.out_w) ((unsigned short *)a.out_w)[pi] = (unsigned short)nh;
             const long long oi = a.out_frame_rows ? (long long)(row - a.row0) * cam.width + col : pi;
-            T *dst = vec ? (T *)&stage[wrp][0] + lane * 3 : (T *)ra.out + oi * ra.channels;
-            remap_pixel_xy<T>(ra, cam, dst, xc, yc, fa32, (unsigned)nh);
+            // two call sites so that each store has a known address space (shared / global) instead of
+            // a generic pointer
+            if (vec) remap_pixel_xy<T>(ra, cam, (T *)&stage[wrp][0] + lane * 3, xc, yc, fa32, (unsigned)nh);
+            else remap_pixel_xy<T>(ra, cam, (T *)ra.out + oi * ra.channels, xc, yc, fa32, (unsigned)nh);
         }
         if (vec) {
             // vec_ok (host): every run of the warp tile is contiguous in the output and starts on a
@@ -376,17 +378,22 @@ static int launch_render_mb(const TraceArgs &a_in, const RemapArgs &ra, const Bi
         static int resident = 0;
         if (!resident) {
             int g = 0;
-            if (lp_grid_for((const void *)lp_render_kernel<true, true, T, MINB, 4>, block, &g) != LP_OK) return LP_ERR_CUDA;
+            if (lp_grid_for((const void *)lp_render_kernel<true, true, T, MINB, 4, true>, block, &g) != LP_OK) return LP_ERR_CUDA;
             resident = g;
         }
         const int span = render_span();
         const long long tickets = (warp_tiles + span - 1) / span;
-        if (chunks > resident && tickets < 0x7fffffffLL - 0x100000) {
+        // (the ticket schedule is instantiated for the default arithmetic only: FMA loop, fast path, 4-step trips)
+        if (chunks > resident && tickets < 0x7fffffffLL - 0x100000 && fused && icmp && render_trip() == 4) {
             static unsigned next_slot = 0;
             a.dyn_tickets = (int32_t)tickets; a.dyn_span = span;
             a.dyn_slot = (int32_t)(__atomic_fetch_add(&next_slot, 1u, __ATOMIC_RELAXED) % LP_TICKET_SLOTS);
             grid = (unsigned)resident;
         }
+    }
+    if (a.dyn_tickets > 0) {
+        lp_render_kernel<true, true, T, MINB, 4, true><<<grid, block, 0, stream>>>(a, ra, c, cam);
+        return lp_check_launch();
     }
     if (fused) {
         if (icmp && render_trip() == 4) lp_render_kernel<true, true, T, MINB, 4><<<grid, block, 0, stream>>>(a, ra, c, cam);
