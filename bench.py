@@ -436,13 +436,47 @@ def run_gpu(args):
     render_local()
     if not torch.equal(tile_hosts[(args.steps - 1) % 3], local_tile.cpu()):
         raise SystemExit("e2e frame differs from the device-resident frame")
+
+    # ---- the same bytes with no kernel: every rank's H2D and D2H copies alone, all ranks at once ----
+    # (what the host side of the box can move; N GPUs share its PCIe root complex / DRAM)
+    def copies_only(k, up=True):
+        n_up = rows * W * 3                      # this rank's share of a new source == its tile, in bytes
+        h_in = torch.empty(n_up, dtype=torch.uint8).pin_memory()
+        d_in = torch.empty(n_up, dtype=torch.uint8, device="cuda")
+        d_out = local_tile.reshape(-1)
+        s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def one(j):
+            if up:
+                with torch.cuda.stream(s_up):
+                    d_in.copy_(h_in, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                tile_hosts[j % 3].reshape(-1).copy_(d_out, non_blocking=True)
+        for j in range(3):
+            one(j)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        s_up.wait_stream(torch.cuda.current_stream())
+        s_dn.wait_stream(torch.cuda.current_stream())
+        for j in range(k):
+            one(j)
+        torch.cuda.current_stream().wait_stream(s_up)
+        torch.cuda.current_stream().wait_stream(s_dn)
+        b.record()
+        barrier()
+        return max_over_ranks(a.elapsed_time(b))
+    total_copies = copies_only(args.steps)
+    total_copies_down = copies_only(args.steps, up=False)
     e2e_static = None
     if N > 1:
         # the same with an UNCHANGED background (parameter sweeps, BASELINE config 5): the source
         # stays resident, a step moves camera parameters in and the tile out
         total_static = timed_e2e(args.steps, version=1)
         e2e_static = {"value": H * W * args.steps / (total_static * 1e-3), "unit": "rays/s",
-                      "ms_per_frame": total_static / args.steps, "h2d_bytes_per_step": 0,
+                      "ms_per_frame": total_static / args.steps,
+                      "copies_only_ms_per_frame": total_copies_down / args.steps, "h2d_bytes_per_step": 0,
                       "d2h_bytes_per_step": int(H * W * 3),
                       "path": "dist.ShardedHostFrames with an unchanged source version: no upload, no all-gather"}
 
@@ -483,6 +517,10 @@ def run_gpu(args):
             "ms_per_frame": total_ms / args.steps,
             "e2e": {"value": rays * args.steps / (total_e2e * 1e-3), "unit": "rays/s",
                     "ms_per_frame": total_e2e / args.steps,
+                    "copies_only_ms_per_frame": total_copies / args.steps,
+                    "copies_only_host_bytes_per_s": rays * 6 * args.steps / (total_copies * 1e-3),
+                    "copies_only_what": "the same H2D + D2H bytes of every rank with no kernel in between, all ranks "
+                                        "at once (max over ranks): the host-side floor of this box for the e2e leg",
                     "h2d_bytes_per_step": int(rays * 3), "d2h_bytes_per_step": int(rays * 3),
                     "path": ("image_lens.HostFramePipeline: pinned uint8 source -> H2D -> lp_render_frame -> D2H "
                              "pinned uint8 frame, every frame; 3 slots on 3 streams")
@@ -500,8 +538,11 @@ def run_gpu(args):
             "roofline": fp64_roofline("lp_render_kernel (alpha + Binet RK4 + remap, fused)", flops_max_tile, kern_ms,
                                       peak_tf, ncu_traffic(),
                                       "43 flop per RK4 step + 40 per ray (SURVEY.md 8d), the reference's own operation "
-                                      "count; the hybrid loop issues 22 FP64-pipe slots per step (strict: 34, ceiling "
-                                      "0.5 by construction)"),
+                                      "count; the hybrid loop issues 18 FP64 instructions per step (second-order form of "
+                                      "the same RK4 step; strict: 34, ceiling 0.5 by construction).  The kernel is bound by "
+                                      "the SM sub-partition's issue port: an FP64 instruction holds it for 2 cycles, any "
+                                      "other for 1, and 2 x FP64 + other instructions = the elapsed cycles (ncu, "
+                                      "profiles/r2o_ncu_render_u8.md: issue active 64.6 % + FP64 pipe 74 % / 2 = 101.6 %)"),
             "kernel_ms_per_step": stat(ms_k),
             "rk4_steps_per_frame": sum_steps,
             "lane_efficiency": sum_steps / sum_warp if sum_warp else None,
@@ -792,14 +833,15 @@ def single_gpu_records(args, torch, il, dev, metric, ext, timed, src8_host, fov,
         "config3_rk45_frame_4k": {"ms": t_rk45, "rays_per_s": rays / t_rk45 * 1e3,
                                   "step_attempts_per_s": rk_attempts / t_rk45 * 1e3,
                                   "what": "geodesic_tracer.trace_ray semantics (scipy RK45, rtol 1e-8) for every "
-                                          "pixel of the 3840x2160 alpha table, lp_rk45_kernel"},
-        "roofline_rk45": {"bound": "fp64", "kernel": "lp_rk45_kernel", "achieved": rk_tf, "peak": peak_tf,
+                                          "pixel of the 3840x2160 alpha table, lp_rk45_eq_kernel (equatorial observer: four moving components)"},
+        "roofline_rk45": {"bound": "fp64", "kernel": "lp_rk45_eq_kernel", "achieved": rk_tf, "peak": peak_tf,
                           "unit": "TFLOP/s", "frac": rk_tf / peak_tf, "frac_of_nominal": rk_tf / FP64_NOMINAL_TF,
                           "kernel_ms": t_rk45, "step_attempts": rk_attempts,
-                          "flop_model": "%d FP64-pipe instructions per step attempt as compiled (DESIGN.md §4 recount: 6 "
-                                        "RHS evaluations, stage / error sums, controller) x 2 flop; SURVEY 8d's "
-                                        "estimate was ~750 flop per attempt" % rk_slots,
-                          "traffic": ncu_traffic("lp_rk45_kernel"), "traffic_source": TRAFFIC_SOURCE},
+                          "flop_model": "%d FP64 instructions per step attempt and ray as executed by the equatorial "
+                                        "four-component kernel (ncu recount, see RK45_FP64_SLOTS_PER_ATTEMPT in bench.py: 6 RHS "
+                                        "evaluations, stage / error sums, controller) x 2 flop; the eight-component kernel "
+                                        "executed 620, SURVEY 8d's estimate was ~750 flop per attempt" % rk_slots,
+                          "traffic": ncu_traffic("lp_rk45_eq_kernel"), "traffic_source": TRAFFIC_SOURCE},
         "kerr_lookup_4k": {"ms": t_kerr, "rays_per_s": rays / t_kerr * 1e3, "ms_api_with_mirror": t_kerr_api,
                            "what": "Kerr a=0.9 M, equatorial observer: (alpha, theta) lookup of the full 3840x2160 "
                                    "frame without the top/bottom mirror, lp_kerr_queued_kernel; ms_api_with_mirror = "
@@ -827,9 +869,13 @@ def single_gpu_records(args, torch, il, dev, metric, ext, timed, src8_host, fov,
     }
 
 
-# FP64-pipe instructions per step attempt of the two adaptive integrators, from the SASS of the
-# kernels as compiled (tools/count_fp64_slots.py)
-RK45_FP64_SLOTS_PER_ATTEMPT = 620
+# FP64-pipe instructions per step attempt (per ray) of the two adaptive integrators as executed:
+#   RK45 — the equatorial four-component kernel lp_rk45_eq_kernel: ncu (profiles/r2_ncu_rk45.md, 960x540 rays,
+#          293.4 attempts per ray): FP64 pipe active 55.81 % of 12 315 639 cycles on 592 sub-partitions at 2
+#          cycles per warp instruction = 2.034e9 warp instructions x 27.81 active threads / 1.521e8 attempts = 372
+#          (the eight-component kernel it replaced: 620);
+#   Kerr — 7 right-hand sides of 204 FP64 instructions + 370 of stage / error sums, from the SASS.
+RK45_FP64_SLOTS_PER_ATTEMPT = 372
 KERR_FP64_SLOTS_PER_ATTEMPT = 1600
 
 
