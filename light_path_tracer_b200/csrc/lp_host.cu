@@ -93,6 +93,12 @@ int lp_make_binet_consts(double M, double R_S, double r_obs, double phi_max, dou
     c->inv_sqrt_f0 = 1.0 / c->sqrt_f0;
     c->inv_ue_sq = 1.0 / c->ue_sq;
     c->div_const_ok = div_const_exact(c->sqrt_f0) && div_const_exact(c->ue_sq);
+    // the FMA loop's scaled variable v = 3M u (lp_internal.cuh, rk4_step)
+    c->v0 = c->M3 * c->u0;
+    c->vc = c->M3 * c->uc;
+    c->ve = c->M3 * c->ue;
+    c->inv_M3 = 1.0 / c->M3;
+    c->scaled_ok = (c->M3 > 1e-100 && c->M3 < 1e100 && isfinite(c->inv_M3)) ? 1 : 0;
 
     // replay the phi bookkeeping of the while-loop (metrics.py:72-78, :93, :115)
     int shift = 0;
@@ -138,6 +144,19 @@ int lp_binet_fast_ok(const BinetConsts *c)
     unsigned long long bc, be;
     memcpy(&bc, &c->uc, 8);
     memcpy(&be, &c->ue, 8);
+    const unsigned hc = (unsigned)(bc >> 32), he = (unsigned)(be >> 32);
+    return hc > he + 1u;
+}
+
+// The same for a kernel that runs the FMA loop (scaled band) and the strict re-trace (plain band).
+int lp_binet_fast_ok_fused(const BinetConsts *c)
+{
+    if (!c->scaled_ok || !lp_binet_fast_ok(c)) return 0;
+    if (!(c->vc > 0.0) || !(c->ve > 0.0) || !isfinite(c->vc) || !isfinite(c->ve)) return 0;
+    if (!(c->ve < c->v0 && c->v0 < c->vc)) return 0;
+    unsigned long long bc, be;
+    memcpy(&bc, &c->vc, 8);
+    memcpy(&be, &c->ve, 8);
     const unsigned hc = (unsigned)(bc >> 32), he = (unsigned)(be >> 32);
     return hc > he + 1u;
 }

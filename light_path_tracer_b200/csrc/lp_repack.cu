@@ -70,15 +70,15 @@ __device__ __forceinline__ void rp_finish_ray(const BinetConsts &c, const LoopRe
         bool crossed = false;
         double u1, w1;
         for (; k < L.n_full; ++k) {
-            rk4_step<FUSED>(u, w, M3, h, hh, h6, u1, w1);
-            if (u1 >= c.uc) { status = -1; crossed = true; }
-            else if (u1 <= c.ue) { status = 1; crossed = true; }
+            rk4_full_step<FUSED>(L, u, w, u1, w1);
+            if (u1 >= band_hi<FUSED>(c)) { status = -1; crossed = true; }
+            else if (u1 <= band_lo<FUSED>(c)) { status = 1; crossed = true; }
             if (crossed) { up = u; wp = w; u = u1; w = w1; break; }
             u = u1; w = w1;
         }
         if (crossed) {
             r.steps = k + 1;
-            binet_cross(status == -1 ? c.uc : c.ue, h, binet_phi_at(c, k), up, wp, u, w, phi);
+            binet_cross_s<FUSED>(c, status == -1, h, binet_phi_at(c, k), up, wp, u, w, phi);
         } else {
             r.steps = L.n_full;
             phi = c.phi_end;
@@ -87,18 +87,19 @@ __device__ __forceinline__ void rp_finish_ray(const BinetConsts &c, const LoopRe
                 up = u; wp = w;
                 rk4_step<FUSED>(up, wp, M3, hj, mul_(0.5, hj), __ddiv_rn(hj, 6.0), u, w);
                 r.steps++;
-                if (u >= c.uc) { status = -1; binet_cross(c.uc, hj, c.tail_phi[j], up, wp, u, w, phi); break; }
-                if (u <= c.ue) { status = 1; binet_cross(c.ue, hj, c.tail_phi[j], up, wp, u, w, phi); break; }
+                if (u >= band_hi<FUSED>(c)) { status = -1; binet_cross_s<FUSED>(c, true, hj, c.tail_phi[j], up, wp, u, w, phi); break; }
+                if (u <= band_lo<FUSED>(c)) { status = 1; binet_cross_s<FUSED>(c, false, hj, c.tail_phi[j], up, wp, u, w, phi); break; }
             }
+            if (status == 2) binet_scale_out<FUSED>(c, u, w);
         }
     } else {
         const bool cap = (code == RP_CAPTURE);
         status = cap ? -1 : 1;
         r.steps = k + 1;
-        binet_cross(cap ? c.uc : c.ue, L.h, binet_phi_at(c, k), up, wp, u, w, phi);
+        binet_cross_s<FUSED>(c, cap, L.h, binet_phi_at(c, k), up, wp, u, w, phi);
     }
     binet_finish(c, status, phi, u, w, r);
-    if (FUSED && r.steps > retrace_steps) binet_trace<false, true>(c, L, alpha, r);     // LP_TRACE_HYBRID
+    if (FUSED && r.steps > retrace_steps) binet_trace<false, true>(c, load_loop_regs<false>(c), alpha, r);     // LP_TRACE_HYBRID
 }
 
 // per-warp frame statistics (shared memory; filled by warp reductions in the finish phase so that
@@ -115,7 +116,7 @@ lp_render_repack_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts
 {
     extern __shared__ __align__(16) unsigned char rp_smem[];
     __shared__ RpStats rp_stats[LP_RP_WARPS];
-    const LoopRegs L = load_loop_regs(c);
+    const LoopRegs L = load_loop_regs<FUSED>(c);
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     const unsigned full = 0xffffffffu;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -146,6 +147,7 @@ lp_render_repack_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts
     const double M3 = L.M3, h = L.h, hh = L.hh, h6 = L.h6;
     const unsigned lo_hi = L.lo_hi, span = L.span;
     const int n_full = L.n_full;
+    const double b_hi = band_hi<FUSED>(c), b_lo = band_lo<FUSED>(c);
 
     // Each phase appears ONCE in the code (the kernel is instruction-cache sensitive: the finish
     // phase with its strict re-trace is ~5 k instructions).  Capacity of the out-queue: exit
@@ -247,6 +249,7 @@ lp_render_repack_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts
                 const int s = in_head + rank;
                 w = q.in_w0[s]; pix = q.in_pix[s]; a32 = q.in_a32[s];
                 u = c.u0; k = 0; code = -1;
+                binet_scale_in<FUSED>(c, u, w);          // the FMA loop carries 3M u (rk4_step)
             }
             const int taken = min(__popc(need), in_count);
             in_head += taken;
@@ -268,10 +271,10 @@ lp_render_repack_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts
                 int xcode = -1;
                 if (k + 4 <= n_full) {
                     double u1, w1, u2, w2, u3, w3, u4, w4;
-                    rk4_step<FUSED>(u, w, M3, h, hh, h6, u1, w1);
-                    rk4_step<FUSED>(u1, w1, M3, h, hh, h6, u2, w2);
-                    rk4_step<FUSED>(u2, w2, M3, h, hh, h6, u3, w3);
-                    rk4_step<FUSED>(u3, w3, M3, h, hh, h6, u4, w4);
+                    rk4_full_step<FUSED>(L, u, w, u1, w1);
+                    rk4_full_step<FUSED>(L, u1, w1, u2, w2);
+                    rk4_full_step<FUSED>(L, u2, w2, u3, w3);
+                    rk4_full_step<FUSED>(L, u3, w3, u4, w4);
                     const unsigned t1 = (unsigned)__double2hiint(u1) - lo_hi;
                     const unsigned t2 = (unsigned)__double2hiint(u2) - lo_hi;
                     const unsigned t3 = (unsigned)__double2hiint(u3) - lo_hi;
@@ -279,14 +282,14 @@ lp_render_repack_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts
                     int which = 0;
                     bool cap = false;
                     if (max(max(t1, t2), max(t3, t4)) >= span) {
-                        if (u1 >= c.uc) { which = 1; cap = true; }
-                        else if (u1 <= c.ue) { which = 1; }
-                        else if (u2 >= c.uc) { which = 2; cap = true; }
-                        else if (u2 <= c.ue) { which = 2; }
-                        else if (u3 >= c.uc) { which = 3; cap = true; }
-                        else if (u3 <= c.ue) { which = 3; }
-                        else if (u4 >= c.uc) { which = 4; cap = true; }
-                        else if (u4 <= c.ue) { which = 4; }
+                        if (u1 >= b_hi) { which = 1; cap = true; }
+                        else if (u1 <= b_lo) { which = 1; }
+                        else if (u2 >= b_hi) { which = 2; cap = true; }
+                        else if (u2 <= b_lo) { which = 2; }
+                        else if (u3 >= b_hi) { which = 3; cap = true; }
+                        else if (u3 <= b_lo) { which = 3; }
+                        else if (u4 >= b_hi) { which = 4; cap = true; }
+                        else if (u4 <= b_lo) { which = 4; }
                     }
                     if (which == 0) { u = u4; w = w4; k += 4; }
                     else {
@@ -387,7 +390,7 @@ static int launch_repack_t(const TraceArgs &a, const RemapArgs &ra, const BinetC
 int lp_launch_render_repack(const TraceArgs &a, const RemapArgs &ra, const BinetConsts &c, const CamConsts &cam,
                             int src_dtype, uint32_t flags, cudaStream_t stream)
 {
-    const bool fused = (flags & (LP_TRACE_FUSED | LP_TRACE_HYBRID)) != 0;
+    const bool fused = (flags & (LP_TRACE_FUSED | LP_TRACE_HYBRID)) != 0 && c.scaled_ok;
     switch (src_dtype) {
     case LP_DTYPE_U8: return launch_repack_t<unsigned char>(a, ra, c, cam, fused, stream);
     case LP_DTYPE_F32: return launch_repack_t<float>(a, ra, c, cam, fused, stream);

@@ -44,7 +44,7 @@ template <bool FUSED, bool FAST, int SRC, bool WIDE>
 __global__ void __launch_bounds__(LP_TRACE_BLOCK)
 lp_trace_kernel(const TraceArgs a, const BinetConsts c, const CamConsts cam)
 {
-    const LoopRegs L = load_loop_regs(c);
+    const LoopRegs L = load_loop_regs<FUSED>(c);
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < a.n;
     RayResult r;
@@ -65,7 +65,7 @@ lp_trace_kernel(const TraceArgs a, const BinetConsts c, const CamConsts cam)
             alpha = (double)a32;
         }
         binet_trace<FUSED, FAST, (FUSED && FAST) ? LP_RENDER_DEFAULT_TRIP : 2>(c, L, alpha, r);
-        if (FUSED && r.steps > a.retrace_steps) binet_trace<false, FAST>(c, L, alpha, r);
+        if (FUSED && r.steps > a.retrace_steps) binet_trace<false, FAST>(c, load_loop_regs<false>(c), alpha, r);   // cold: its own constants
         const double fa = (r.status == 1) ? r.fa : __longlong_as_double(0x7ff8000000000000LL);
         if (WIDE) {
             ((double *)a.out_fa)[i] = fa;                          // metrics.py:667
@@ -103,8 +103,9 @@ static int launch_trace(const TraceArgs &a, const BinetConsts &c, const CamConst
                         uint32_t flags, cudaStream_t stream)
 {
     if (a.n == 0) return LP_OK;
-    const bool fused = (flags & (LP_TRACE_FUSED | LP_TRACE_HYBRID)) != 0;
-    const bool icmp = lp_binet_fast_ok(&c) != 0;
+    // the FMA loop integrates 3M u: without a usable scale (c.scaled_ok) the request runs strictly
+    const bool fused = (flags & (LP_TRACE_FUSED | LP_TRACE_HYBRID)) != 0 && c.scaled_ok;
+    const bool icmp = (fused ? lp_binet_fast_ok_fused(&c) : lp_binet_fast_ok(&c)) != 0;
     const int block = trace_block_size();
     const long long chunks = (a.n + block - 1) / block;
     if (chunks > 0x7fffffffLL) return LP_ERR_UNSUPPORTED;
@@ -238,7 +239,7 @@ template <bool FUSED, bool FAST, typename T, int MINB, int TRIP, bool DYN = fals
 __global__ void __launch_bounds__(LP_TRACE_BLOCK, MINB)
 lp_render_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts c, const CamConsts cam)
 {
-    const LoopRegs L = load_loop_regs(c);
+    const LoopRegs L = load_loop_regs<FUSED>(c);
     // RGB (float32 or 8-bit) into an aligned tile: the warp's 32 pixels — tile_h runs of 32 / tile_h
     // consecutive pixels — are staged in shared memory and leave as 16-byte (8-byte for 24-byte runs)
     // vector stores instead of 96 4-byte / 1-byte ones: full sectors, which is what peer (NVLink)
@@ -278,7 +279,7 @@ lp_render_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts c, con
             const double xc = cam_x(cam, col), yc = cam_y(cam, row);     // also the remap's (kept across the loop)
             const float a32 = (float)pixel_alpha64(cam, xc, yc);
             binet_trace<FUSED, FAST, TRIP>(c, L, (double)a32, r);
-            if (FUSED && r.steps > a.retrace_steps) binet_trace<false, FAST>(c, L, (double)a32, r);
+            if (FUSED && r.steps > a.retrace_steps) binet_trace<false, FAST>(c, load_loop_regs<false>(c), (double)a32, r);   // cold
             const float fa32 = (float)((r.status == 1) ? r.fa : __longlong_as_double(0x7ff8000000000000LL));
             const long long nh = r.nh < 0 ? 0 : (r.nh > 65535 ? 65535 : r.nh);
             if (a.out_fa) ((float *)a.out_fa)[pi] = fa32;
@@ -363,8 +364,8 @@ template <typename T, int MINB>
 static int launch_render_mb(const TraceArgs &a_in, const RemapArgs &ra, const BinetConsts &c,
                             const CamConsts &cam, uint32_t flags, cudaStream_t stream)
 {
-    const bool fused = (flags & (LP_TRACE_FUSED | LP_TRACE_HYBRID)) != 0;
-    const bool icmp = lp_binet_fast_ok(&c) != 0;
+    const bool fused = (flags & (LP_TRACE_FUSED | LP_TRACE_HYBRID)) != 0 && c.scaled_ok;
+    const bool icmp = (fused ? lp_binet_fast_ok_fused(&c) : lp_binet_fast_ok(&c)) != 0;
     const int block = trace_block_size();
     const long long chunks = (a_in.n + block - 1) / block;
     if (chunks > 0x7fffffffLL) return LP_ERR_UNSUPPORTED;
@@ -488,7 +489,8 @@ extern "C" int lp_render_frame_bands(const void *src, int32_t src_dtype, int32_t
     cudaStream_t st = (cudaStream_t)stream;
     // opt-in lane re-packing schedule; it needs the fast-path precondition (observer strictly inside
     // the integration band), otherwise the request falls through to the default kernel
-    if ((flags & LP_TRACE_REPACK) && lp_binet_fast_ok(&c) && c.valid && n <= 0x7fffffffLL) {
+    const bool rp_fused = (flags & (LP_TRACE_FUSED | LP_TRACE_HYBRID)) != 0 && c.scaled_ok;
+    if ((flags & LP_TRACE_REPACK) && (rp_fused ? lp_binet_fast_ok_fused(&c) : lp_binet_fast_ok(&c)) && c.valid && n <= 0x7fffffffLL) {
         ra.vec_ok = (contiguous32 && ((uintptr_t)out % 16) == 0) ? 1 : 0;   // chunks are staged by construction
         return lp_launch_render_repack(a, ra, c, cam, src_dtype, flags, st);
     }

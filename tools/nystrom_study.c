@@ -77,9 +77,50 @@ static int orbit(int mode, double M, double R_S, double r_obs, double alpha, dou
     }
     *phi_o = phi; *u_o = u; *w_o = w; *steps_o = steps; return status;
 }
+
+// mode 4: the Nystrom step in the SCALED variable v = 3M u (v'' = -v + v^2): g is ONE fma, 14 fp64
+// operations per step.  The loop state, the band test and the exit are in v; the crossing interpolation
+// is the reference's, on the un-scaled values.
+static int orbit_scaled(double M, double R_S, double r_obs, double alpha, double *phi_o, double *u_o, double *w_o, int *steps_o)
+{
+    double f0 = 1.0 - R_S / r_obs; double b = r_obs * sin(alpha) / sqrt(f0); if (b == 0.0) return 0;
+    double u = 1.0 / r_obs; double w0 = 1.0 / (b * b) - u * u + 2.0 * M * u * u * u; if (w0 < 0) return 0; double w = sqrt(w0);
+    double phi = 0, uc = 1.0 / (R_S * 1.01), ue = 1.0 / (2.0 * r_obs); int status = 2; int steps = 0;
+    const double h = 0.05, hh = 0.5 * h, h6 = h / 6.0, M3 = 3.0 * M, iM3 = 1.0 / M3;
+    const double hh2 = hh * hh, h2_2 = h * hh, h2_6 = h * h6;
+    const double VC = M3 * uc, VE = M3 * ue;
+    double v = M3 * u, wv = M3 * w;
+    while (phi < 50.0) {
+        double rem = 50.0 - phi; double hs = h; if (rem < hs) hs = rem; if (hs <= 0) break;
+        if (hs != h) { fprintf(stderr, "short step\n"); exit(1); }
+        double vp = v, wvp = wv;
+        const double k1 = fma(v, v, -v);
+        const double va = fma(hh, wv, v);
+        const double k2 = fma(va, va, -va);
+        const double vb = fma(hh2, k1, va);
+        const double k3 = fma(vb, vb, -vb);
+        const double vhw = fma(h, wv, v);
+        const double vcc = fma(h2_2, k2, vhw);
+        const double k4 = fma(vcc, vcc, -vcc);
+        const double p = k2 + k3;
+        const double s3 = k1 + p;
+        v = fma(h2_6, s3, vhw);
+        wv = fma(h6, (s3 + p) + k4, wvp);
+        steps++;
+        if (v >= VC || v <= VE) {
+            double up = vp * iM3, wp = wvp * iM3; u = v * iM3; w = wv * iM3;
+            double tg = v >= VC ? uc : ue;
+            double d = u - up; double fr = d == 0 ? 1 : (tg - up) / d; if (fr < 0) fr = 0; if (fr > 1) fr = 1;
+            phi += fr * hs; w = wp + fr * (w - wp); u = tg; status = v >= VC ? -1 : 1; break;
+        }
+        phi += hs;
+    }
+    if (status == 2) { u = v * iM3; w = wv * iM3; }
+    *phi_o = phi; *u_o = u; *w_o = w; *steps_o = steps; return status;
+}
 static int ray(int mode, double M, double r_obs, double alpha, double *fa, long *nh, int *steps)
 {
-    double phi, u, w; int st = orbit(mode, M, 2 * M, r_obs, alpha, &phi, &u, &w, steps); if (st == 0) { *fa = NAN; *nh = 0; return 0; }
+    double phi, u, w; int st = mode == 4 ? orbit_scaled(M, 2 * M, r_obs, alpha, &phi, &u, &w, steps) : orbit(mode, M, 2 * M, r_obs, alpha, &phi, &u, &w, steps); if (st == 0) { *fa = NAN; *nh = 0; return 0; }
     double r = 1.0 / u; *nh = (long)floor(fabs(phi) / PI); if (st == -1 || r <= 2.2 * M) { *fa = NAN; return -1; }
     double dr = -w / (u * u); double hy = dr * sin(phi) + r * cos(phi), hx = dr * cos(phi) - r * sin(phi); double c = -cos(atan2(hy, hx)); if (c > 1) c = 1; if (c < -1) c = -1; *fa = acos(c); return 1;
 }
@@ -89,10 +130,10 @@ int main(int argc, char **argv)
     long N = argc > 1 ? atol(argv[1]) : 4000000;
     for (int ir = 0; ir < 8; ir++) {
         double r_obs = robs[ir]; double M = 1; double ac = asin(3 * sqrt(3.0) * sqrt(1 - 2 / r_obs) / r_obs);
-        double maxrel[3][40] = {{0}}; long cnt[40] = {0}; long flips[3] = {0, 0, 0}, nhdiff[3] = {0, 0, 0}; int flipmin[3] = {100000, 100000, 100000};
+        double maxrel[4][40] = {{0}}; long cnt[40] = {0}; long flips[4] = {0, 0, 0, 0}, nhdiff[4] = {0, 0, 0, 0}; int flipmin[4] = {100000, 100000, 100000, 100000};
 #pragma omp parallel
         {
-            double lmax[3][40] = {{0}}; long lcnt[40] = {0}; long lfl[3] = {0, 0, 0}, lnh[3] = {0, 0, 0}; int lmin[3] = {100000, 100000, 100000};
+            double lmax[4][40] = {{0}}; long lcnt[40] = {0}; long lfl[4] = {0, 0, 0, 0}, lnh[4] = {0, 0, 0, 0}; int lmin[4] = {100000, 100000, 100000, 100000};
 #pragma omp for schedule(dynamic, 4096)
             for (long i = 0; i < N; i++) {
                 double t = (double)i / N; double alpha;
@@ -100,7 +141,7 @@ int main(int argc, char **argv)
                 if (r_obs < 3.0 * M + 1e-9 || !(alpha < PI)) continue;
                 double fa0; long n0; int s0; int st0 = ray(0, M, r_obs, alpha, &fa0, &n0, &s0);
                 int bin = s0 / 25; if (bin > 39) bin = 39; lcnt[bin]++;
-                for (int m = 1; m <= 3; m++) {
+                for (int m = 1; m <= 4; m++) {
                     double fa; long n; int s; int st = ray(m, M, r_obs, alpha, &fa, &n, &s);
                     int sm = s < s0 ? s : s0;
                     if (st != st0) { lfl[m - 1]++; if (sm < lmin[m - 1]) lmin[m - 1] = sm; }
@@ -110,13 +151,13 @@ int main(int argc, char **argv)
             }
 #pragma omp critical
             {
-                for (int m = 0; m < 3; m++) { flips[m] += lfl[m]; nhdiff[m] += lnh[m]; if (lmin[m] < flipmin[m]) flipmin[m] = lmin[m];
+                for (int m = 0; m < 4; m++) { flips[m] += lfl[m]; nhdiff[m] += lnh[m]; if (lmin[m] < flipmin[m]) flipmin[m] = lmin[m];
                     for (int b = 0; b < 40; b++) if (lmax[m][b] > maxrel[m][b]) maxrel[m][b] = lmax[m][b]; }
                 for (int b = 0; b < 40; b++) cnt[b] += lcnt[b];
             }
         }
-        printf("r_obs=%g  F: flips=%ld nhdiff=%ld shortest=%d | N: flips=%ld nhdiff=%ld shortest=%d | N2: flips=%ld nhdiff=%ld shortest=%d\n", r_obs, flips[0], nhdiff[0], flipmin[0], flips[1], nhdiff[1], flipmin[1], flips[2], nhdiff[2], flipmin[2]);
-        for (int b = 0; b < 40; b++) if (cnt[b]) printf("  steps %4d-%4d n=%8ld  maxrel F=%.3e  N=%.3e  N2=%.3e\n", b * 25, b * 25 + 24, cnt[b], maxrel[0][b], maxrel[1][b], maxrel[2][b]);
+        printf("r_obs=%g  F: flips=%ld nhdiff=%ld shortest=%d | N: flips=%ld nhdiff=%ld shortest=%d | N2: flips=%ld nhdiff=%ld shortest=%d | V: flips=%ld nhdiff=%ld shortest=%d\n", r_obs, flips[0], nhdiff[0], flipmin[0], flips[1], nhdiff[1], flipmin[1], flips[2], nhdiff[2], flipmin[2], flips[3], nhdiff[3], flipmin[3]);
+        for (int b = 0; b < 40; b++) if (cnt[b]) printf("  steps %4d-%4d n=%8ld  maxrel F=%.3e  N=%.3e  N2=%.3e  V=%.3e\n", b * 25, b * 25 + 24, cnt[b], maxrel[0][b], maxrel[1][b], maxrel[2][b], maxrel[3][b]);
         fflush(stdout);
     }
     return 0;
