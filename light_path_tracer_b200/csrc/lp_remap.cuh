@@ -62,8 +62,15 @@ __device__ __forceinline__ long long pymod(long long a, long long n)
 // are the normalised components themselves, so here (st, ct) = (A, B)/hypot(A, B) with
 // A, B the dot products of the UN-normalised ray (x_cam, y_cam, 1): no arctan2, no second
 // sincos, no normalisation of v.  Straight-line code (see the helpers above).
+//
+// DIR (the fused frame kernel): the tracer has just formed c = cos(fa), s = sin(fa) of the fp64 final_alpha
+// fa (RayResult::cf, sf, fa).  The lookup holds fa32 = float32(fa), so the angle the reference takes the
+// sine and cosine of is fa + d with d = fa32 - fa, |d| <= 3e-8 fa: cos(fa32) = c - s d, sin(fa32) = s + c d
+// up to d^2 / 2 < 5e-16 — far inside the 1e-12 the source index needs — instead of a second sincos.
+template <bool DIR = false>
 __device__ __forceinline__ bool source_coords_xy(const CamConsts &cam, double xc, double yc, float fa32,
-                                                 double &px, double &py)
+                                                 double &px, double &py,
+                                                 double fa64 = 0.0, double cfa = 0.0, double sfa = 0.0)
 {
     const double A = fma(xc, cam.ex0, fma(yc, cam.ex1, cam.ex2));
     const double B = fma(xc, cam.ey0, fma(yc, cam.ey1, cam.ey2));
@@ -72,7 +79,13 @@ __device__ __forceinline__ bool source_coords_xy(const CamConsts &cam, double xc
     const double inv = fast_rsqrt(on_axis ? 1.0 : n2);
     const double st = on_axis ? 0.0 : A * inv, ct = on_axis ? 1.0 : B * inv;
     double sf, cf;
-    sincos_moderate((double)fa32, sf, cf);                  // image_lens.py:340-346
+    if (DIR) {
+        const double d = (double)fa32 - fa64;
+        cf = fma(-sfa, d, cfa);
+        sf = fma(cfa, d, sfa);
+    } else {
+        sincos_moderate((double)fa32, sf, cf);              // image_lens.py:340-346
+    }
     const double tx = fma(st, cam.ex0, ct * cam.ey0);
     const double ty = fma(st, cam.ex1, ct * cam.ey1);
     const double tz = fma(st, cam.ex2, ct * cam.ey2);
@@ -93,10 +106,11 @@ __device__ __forceinline__ bool source_coords(const CamConsts &cam, int row, int
     return source_coords_xy(cam, cam_x(cam, col), cam_y(cam, row), fa32, px, py);
 }
 
-// xc, yc: the pixel's camera-plane coordinates cam_x(col), cam_y(row)
-template <typename T>
+// xc, yc: the pixel's camera-plane coordinates cam_x(col), cam_y(row); DIR: see source_coords_xy
+template <typename T, bool DIR = false>
 __device__ __forceinline__ void remap_pixel_xy(const RemapArgs &a, const CamConsts &cam, T *__restrict__ dst,
-                                               double xc, double yc, float fa32, unsigned wnd)
+                                               double xc, double yc, float fa32, unsigned wnd,
+                                               double fa64 = 0.0, double cfa = 0.0, double sfa = 0.0)
 {   // dst: where this pixel's `channels` values go (global memory, or a staging slot)
     const int C = a.channels;
     const T *__restrict__ src = (const T *)a.src;
@@ -113,7 +127,7 @@ __device__ __forceinline__ void remap_pixel_xy(const RemapArgs &a, const CamCons
             return;
         }
         double px, py;
-        const bool front = source_coords_xy(cam, xc, yc, fa32, px, py);
+        const bool front = source_coords_xy<DIR>(cam, xc, yc, fa32, px, py, fa64, cfa, sfa);
         const int H = cam.height, W = cam.width;
         int ix = __double2int_rn(px), iy = __double2int_rn(py);
         bool ok;
@@ -147,7 +161,7 @@ __device__ __forceinline__ void remap_pixel_xy(const RemapArgs &a, const CamCons
         return;
     }
     double px, py;
-    const bool front = source_coords_xy(cam, xc, yc, fa32, px, py);
+    const bool front = source_coords_xy<DIR>(cam, xc, yc, fa32, px, py, fa64, cfa, sfa);
     const long long H = cam.height, W = cam.width;
     long long ix = (long long)rint(px), iy = (long long)rint(py);   // np.rint -> intp
     bool ok;

@@ -176,7 +176,8 @@ lp_render_repack_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts
                 const long long nh = r.nh < 0 ? 0 : (r.nh > 65535 ? 65535 : r.nh);
                 if (a.out_fa) ((float *)a.out_fa)[i] = fa32;
                 if (a.out_w) ((unsigned short *)a.out_w)[i] = (unsigned short)nh;
-                remap_pixel<T>(ra, cam, stage + (size_t)p * C, row, col, fa32, (unsigned)nh);
+                remap_pixel_xy<T, true>(ra, cam, stage + (size_t)p * C, cam_x(cam, col), cam_y(cam, row), fa32, (unsigned)nh,
+                                        r.fa, r.cf, r.sf);
             }
             if (a.stats) {
                 const unsigned st = mine ? (unsigned)r.steps : 0u;
@@ -224,7 +225,7 @@ lp_render_repack_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts
                     long long oi;
                     tile_pixel(a, cam.width, chunk0 + p, row, col, oi);
                     al = (float)pixel_alpha64(cam, cam_x(cam, col), cam_y(cam, row));
-                    valid = binet_init(c, (double)al, uu, w0);
+                    valid = binet_init<FUSED>(c, (double)al, uu, w0);
                 }
                 const unsigned vm = __ballot_sync(full, valid);
                 const unsigned im = __ballot_sync(full, live && !valid);

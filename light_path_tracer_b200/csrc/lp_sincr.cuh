@@ -33,22 +33,35 @@
 #endif
 #include "lp_sintab.h"
 
+// Polynomial constants of lp_sin_dd.  On the device they sit in the constant bank: an FP64 instruction of
+// sm_100 takes a constant through a uniform register, and an immediate double costs two issue slots
+// (UMOV lo, hi) where a table entry costs half a slot (LDCU.128).
+#ifdef __CUDACC__
+static __constant__ double c_sincr_k[6] = {-0x1.6c16c16c16c17p-10, 0x1.5555555555555p-5, -0x1.a01a01a01a01ap-13,
+                                           0x1.1111111111111p-7, -0x1.5555555555555p-3, -0.00390625};
+#define LP_SINCR_K(i) c_sincr_k[i]
+#else
+static const double lp_sincr_k[6] = {-0x1.6c16c16c16c17p-10, 0x1.5555555555555p-5, -0x1.a01a01a01a01ap-13,
+                                     0x1.1111111111111p-7, -0x1.5555555555555p-3, -0.00390625};
+#define LP_SINCR_K(i) lp_sincr_k[i]
+#endif
+
 // sin(yh + yl) for 0 <= yh <= (LP_SINTAB_N-1)/256, |yl| <= ulp(yh)/2
 LP_SINCR_FN double lp_sin_dd(double yh, double yl)
 {
     const double shifter = 6755399441055744.0;           // 1.5 * 2^52: rint via add/sub
     const double kf = (yh * 256.0 + shifter) - shifter;  // rint(256 yh), exact integer
     const int k = (int)kf;
-    const double t = LP_FMA(kf, -0.00390625, yh);        // yh - k/256, exact
+    const double t = LP_FMA(kf, LP_SINCR_K(5), yh);      // yh - k/256, exact
     const double Sh = lp_sintab[k][0], Sl = lp_sintab[k][1];
     const double Ch = lp_sintab[k][2], Cl = lp_sintab[k][3];
     const double t2 = t * t;
     // cos t - 1 and sin t - t, |t| <= 2^-9
-    double a = LP_FMA(t2, -0x1.6c16c16c16c17p-10, 0x1.5555555555555p-5);
+    double a = LP_FMA(t2, LP_SINCR_K(0), LP_SINCR_K(1));
     a = LP_FMA(t2, a, -0.5);
     const double pc = t2 * a;
-    double b = LP_FMA(t2, -0x1.a01a01a01a01ap-13, 0x1.1111111111111p-7);
-    b = LP_FMA(t2, b, -0x1.5555555555555p-3);
+    double b = LP_FMA(t2, LP_SINCR_K(2), LP_SINCR_K(3));
+    b = LP_FMA(t2, b, LP_SINCR_K(4));
     const double ps = (t * t2) * b;
     // leading terms, exactly: Sh + Ch*t = s + (err + e)
     const double p = Ch * t;

@@ -287,8 +287,8 @@ lp_render_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts c, con
             const long long oi = a.out_frame_rows ? (long long)(row - a.row0) * cam.width + col : pi;
             // two call sites so that each store has a known address space (shared / global) instead of
             // a generic pointer
-            if (vec) remap_pixel_xy<T>(ra, cam, (T *)&stage[wrp][0] + lane * 3, xc, yc, fa32, (unsigned)nh);
-            else remap_pixel_xy<T>(ra, cam, (T *)ra.out + oi * ra.channels, xc, yc, fa32, (unsigned)nh);
+            if (vec) remap_pixel_xy<T, true>(ra, cam, (T *)&stage[wrp][0] + lane * 3, xc, yc, fa32, (unsigned)nh, r.fa, r.cf, r.sf);
+            else remap_pixel_xy<T, true>(ra, cam, (T *)ra.out + oi * ra.channels, xc, yc, fa32, (unsigned)nh, r.fa, r.cf, r.sf);
         }
         if (vec) {
             // vec_ok (host): every run of the warp tile is contiguous in the output and starts on a
