@@ -98,6 +98,9 @@ int lp_make_binet_consts(double M, double R_S, double r_obs, double phi_max, dou
     c->vc = c->M3 * c->uc;
     c->ve = c->M3 * c->ue;
     c->inv_M3 = 1.0 / c->M3;
+    c->hh2 = c->hh * c->hh;
+    c->h2_2 = c->h * c->hh;
+    c->h2_6 = c->h * c->h6;
     c->scaled_ok = (c->M3 > 1e-100 && c->M3 < 1e100 && isfinite(c->inv_M3)) ? 1 : 0;
 
     // replay the phi bookkeeping of the while-loop (metrics.py:72-78, :93, :115)

@@ -78,7 +78,7 @@ __device__ __forceinline__ void rp_finish_ray(const BinetConsts &c, const LoopRe
         }
         if (crossed) {
             r.steps = k + 1;
-            binet_cross_s<FUSED>(c, status == -1, h, binet_phi_at(c, k), up, wp, u, w, phi);
+            binet_cross_s<FUSED>(c, status == -1, h, binet_phi_at<FUSED>(c, k), up, wp, u, w, phi);
         } else {
             r.steps = L.n_full;
             phi = c.phi_end;
@@ -96,9 +96,9 @@ __device__ __forceinline__ void rp_finish_ray(const BinetConsts &c, const LoopRe
         const bool cap = (code == RP_CAPTURE);
         status = cap ? -1 : 1;
         r.steps = k + 1;
-        binet_cross_s<FUSED>(c, cap, L.h, binet_phi_at(c, k), up, wp, u, w, phi);
+        binet_cross_s<FUSED>(c, cap, L.h, binet_phi_at<FUSED>(c, k), up, wp, u, w, phi);
     }
-    binet_finish(c, status, phi, u, w, r);
+    binet_finish<FUSED>(c, status, phi, u, w, r);
     if (FUSED && r.steps > retrace_steps) binet_trace<false, true>(c, load_loop_regs<false>(c), alpha, r);     // LP_TRACE_HYBRID
 }
 

@@ -46,8 +46,9 @@ static const double lp_sincr_k[6] = {-0x1.6c16c16c16c17p-10, 0x1.5555555555555p-
 #define LP_SINCR_K(i) lp_sincr_k[i]
 #endif
 
-// sin(yh + yl) for 0 <= yh <= (LP_SINTAB_N-1)/256, |yl| <= ulp(yh)/2
-LP_SINCR_FN double lp_sin_dd(double yh, double yl)
+// sin(yh + yl) for 0 <= yh <= (LP_SINTAB_N-1)/256, |yl| <= ulp(yh)/2; has_lo = 0: yl is zero (the low-word
+// term is skipped: the compiler cannot drop a multiplication by a zero it has to treat as IEEE)
+LP_SINCR_FN double lp_sin_dd(double yh, double yl, int has_lo)
 {
     const double shifter = 6755399441055744.0;           // 1.5 * 2^52: rint via add/sub
     const double kf = (yh * 256.0 + shifter) - shifter;  // rint(256 yh), exact integer
@@ -69,13 +70,15 @@ LP_SINCR_FN double lp_sin_dd(double yh, double yl)
     const double s = Sh + p;
     const double bb = s - Sh;
     const double err = (Sh - (s - bb)) + (p - bb);       // two-sum
-    // cos(yh) to first order, for the low word of the argument
-    const double cy = LP_FMA(-Sh, t, Ch);
     double corr = LP_FMA(Cl, t, Sl + e);
     corr = corr + err;
     corr = LP_FMA(Sh, pc, corr);
     corr = LP_FMA(Ch, ps, corr);
-    corr = LP_FMA(cy, yl, corr);
+    if (has_lo) {
+        // cos(yh) to first order, for the low word of the argument
+        const double cy = LP_FMA(-Sh, t, Ch);
+        corr = LP_FMA(cy, yl, corr);
+    }
     return s + corr;
 }
 
@@ -89,13 +92,13 @@ LP_SINCR_FN double lp_sin_cr(double x)
 LP_SINCR_FN double lp_sin_cr_pos(double x)
 {
     const double pi_hi = 0x1.921fb54442d18p+1, pi_lo = 0x1.1a62633145c07p-53;
-    if (x >= 0x1.0p-26 && x <= 1.5707963267948966) return lp_sin_dd(x, 0.0);
+    if (x >= 0x1.0p-26 && x <= 1.5707963267948966) return lp_sin_dd(x, 0.0, 0);
     if (x > 1.5707963267948966 && x <= pi_hi) {
         const double d = pi_hi - x;                      // exact (Sterbenz)
         const double yh = d + pi_lo;
         const double bb = yh - d;
         const double yl = (d - (yh - bb)) + (pi_lo - bb);
-        return lp_sin_dd(yh, yl);
+        return lp_sin_dd(yh, yl, 1);
     }
     if (x >= 0.0 && x < 0x1.0p-26) return x;             // sin x = x(1 - x^2/6), rounds to x
     return LP_LIBSIN(x);

@@ -294,19 +294,15 @@ lp_render_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts c, con
             // vec_ok (host): every run of the warp tile is contiguous in the output and starts on a
             // vector boundary.  Vector v of the staged 96 floats / bytes belongs to run v / per_run.
             __syncwarp();
-            const int th = a.tile_h > 1 ? a.tile_h : 1;
-            const int run_bytes = (32 / th) * 3 * (int)sizeof(T);
-            const int vb = (run_bytes % 16 == 0) ? 16 : 8;
-            const int per_run = run_bytes / vb;
             const int r0 = __shfl_sync(0xffffffffu, tr, 0), c0 = __shfl_sync(0xffffffffu, col, 0);
-            if (lane < th * per_run) {
-                const int run = lane / per_run, part = lane - run * per_run;
+            if (lane < a.st_lanes) {
+                const int run = (int)(((unsigned)lane * a.st_magic) >> 16), part = lane - run * a.st_per_run;
                 const int rr = r0 + run;
                 const long long o0 = a.out_frame_rows ? (long long)(tile_row(a, rr) - a.row0) * cam.width + c0
                                                       : (long long)rr * cam.width + c0;
-                unsigned char *g = (unsigned char *)((T *)ra.out + o0 * 3) + part * vb;
-                const unsigned char *sm = (const unsigned char *)stage[wrp] + run * run_bytes + part * vb;
-                if (vb == 16) *reinterpret_cast<uint4 *>(g) = *reinterpret_cast<const uint4 *>(sm);
+                unsigned char *g = (unsigned char *)((T *)ra.out + o0 * 3) + part * a.st_vb;
+                const unsigned char *sm = (const unsigned char *)stage[wrp] + run * a.st_run_bytes + part * a.st_vb;
+                if (a.st_vb == 16) *reinterpret_cast<uint4 *>(g) = *reinterpret_cast<const uint4 *>(sm);
                 else *reinterpret_cast<uint2 *>(g) = *reinterpret_cast<const uint2 *>(sm);
             }
             __syncwarp();      // the staging slots are reused by the warp's next tile
@@ -482,6 +478,15 @@ extern "C" int lp_render_frame_bands(const void *src, int32_t src_dtype, int32_t
     ra.vec_ok = ((flags & LP_RENDER_STAGED_STORES) && channels == 3 && runs_ok &&
                  (src_dtype == LP_DTYPE_F32 || src_dtype == LP_DTYPE_U8 || src_dtype == LP_DTYPE_U8_UNIT) &&
                  ((uintptr_t)out % 16) == 0) ? 1 : 0;
+    {   // write-out geometry of a warp tile (see TraceArgs)
+        const int esz = (src_dtype == LP_DTYPE_F32) ? 4 : (src_dtype == LP_DTYPE_F64) ? 8 : 1;
+        a.st_run_bytes = (32 / th) * 3 * esz;
+        a.st_vb = (a.st_run_bytes % 16 == 0) ? 16 : 8;
+        a.st_per_run = a.st_run_bytes / a.st_vb;
+        a.st_lanes = th * a.st_per_run;
+        a.st_magic = (65536u + (uint32_t)a.st_per_run - 1u) / (uint32_t)a.st_per_run;
+        if (a.st_run_bytes % 8 != 0 || a.st_lanes > 32) ra.vec_ok = 0;
+    }
     ra.u8_scale = (src_dtype == LP_DTYPE_U8_UNIT) ? 255.0f : 1.0f;
     ra.fast3 = (channels == 3 && sampling == LP_SAMPLE_NEAREST &&
                 (long long)cam.height * cam.width * 3 < 0x7fffffffLL) ? 1 : 0;

@@ -36,6 +36,11 @@ struct TraceArgs {
     // frame kernel, ticket schedule (lp_trace.cu): tickets in this launch (0 = static one tile per warp),
     // warp tiles per ticket, counter slot
     int32_t dyn_tickets, dyn_span, dyn_slot;
+    // staged stores of the frame kernel (host-side arithmetic of the warp's write-out, so that the kernel
+    // has no integer division): bytes of one run of the warp tile, vector width (16 / 8), vectors per run,
+    // lanes that store (tile_h * per_run), and ceil(2^16 / per_run) for lane / per_run by multiply-shift
+    int32_t st_run_bytes, st_vb, st_per_run, st_lanes;
+    uint32_t st_magic;
 };
 
 // frame row of tile-local row r (interleaved bands, see above)
