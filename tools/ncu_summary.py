@@ -82,6 +82,40 @@ def launches(csv_path, out_md):
         f.write("\nTotal listed GPU time: %.1f us over %d launches.\n" % (total, sum(len(v) for v in per.values())))
 
 
+FP64_OPS = ("DFMA", "DADD", "DMUL", "DSETP")
+
+
+def source_counts(rep_path):
+    """Executed warp instructions per warp of the (single) kernel in a capture taken with --import-source on:
+    FP64-pipe arithmetic (DFMA / DADD / DMUL / DSETP: each holds the dispatch port for two cycles) and the rest."""
+    raw = subprocess.run(["ncu", "-i", rep_path, "--page", "source", "--csv", "--print-source", "sass"],
+                         capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr = next((r for r in rows if "Instructions Executed" in r and "Source" in r), None)
+    if hdr is None:
+        return None
+    i_src, i_ex = hdr.index("Source"), hdr.index("Instructions Executed")
+    first, f64, oth = None, 0, 0
+    for r in rows[rows.index(hdr) + 1:]:
+        if len(r) <= max(i_src, i_ex) or not r[i_ex].isdigit():
+            continue
+        toks = r[i_src].split()
+        if not toks:
+            continue
+        op = (toks[1] if toks[0].startswith("@") and len(toks) > 1 else toks[0]).split(".")[0]
+        n = int(r[i_ex])
+        if first is None:
+            first = n          # the kernel's first instruction: executed once by every warp
+        if op in FP64_OPS:
+            f64 += n
+        else:
+            oth += n
+    if not first:
+        return None
+    return {"warps": first, "fp64_inst_per_warp": f64 / first, "other_inst_per_warp": oth / first,
+            "issue_cycles_per_warp": (2 * f64 + oth) / first, "source_page": os.path.basename(rep_path)}
+
+
 def report(rep_path, out_md, json_path=None):
     raw = subprocess.run(["ncu", "-i", rep_path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
@@ -112,6 +146,17 @@ def report(rep_path, out_md, json_path=None):
                     "source": os.path.basename(rep_path)}
             except (KeyError, ValueError):
                 pass
+    if len(summary) == 1:
+        sc = source_counts(rep_path)
+        if sc:
+            for v in summary.values():
+                v.update(sc)
+            with open(out_md, "a") as f:
+                f.write("## executed instructions per warp (source page)\n\n| | |\n|---|---|\n")
+                for k in ("warps", "fp64_inst_per_warp", "other_inst_per_warp", "issue_cycles_per_warp"):
+                    f.write("| %s | %.1f |\n" % (k, sc[k]))
+                f.write("\nissue_cycles_per_warp = 2 x FP64 + other (an FP64 instruction holds the sub-partition's dispatch "
+                        "port for two cycles); x warps / 592 sub-partitions = the kernel's elapsed cycles to ~1 %.\n")
     if json_path:
         old = {}
         if os.path.exists(json_path):
