@@ -415,12 +415,15 @@ __device__ __forceinline__ void kerr_trip(double (&state)[5], double (&k1)[5], d
                 if (h < h_min) done = 2;
             } else {
                 const double err_sq = kerr_err_sq(state, nxt, k1, k3, k4, k5, k6, k7, h, atol, rtol);
-                const double err_norm = __dsqrt_rn(err_sq / 5.0);
-                // 0.9 * err_norm ** -0.2 feeds both the reject (metrics.py:517) and the accept
-                // (metrics.py:562) controller: one pow for the whole warp instead of one per
-                // divergent branch
-                const double pow_term = 0.9 * pow(err_norm, -0.2);
-                if (err_norm > 1.0) {                                    // reject, metrics.py:516-522
+                // err_norm = sqrt(err_sq / 5) (metrics.py:514) only enters comparisons with constants and
+                // 0.9 * err_norm ** -0.2, which feeds both the reject (metrics.py:517) and the accept
+                // (metrics.py:562) controller: the controller works on the square, e2 = err_norm^2, and
+                // 0.9 * e2^-0.1 comes from inv_tenth_root (lp_internal.cuh) instead of a square root, a
+                // division and pow() — a few ulp, like the difference between CUDA's pow and the host's
+                const double e2 = err_sq * 0.2;
+                double pow_term = 0.9 * inv_tenth_root(e2);
+                if (!(err_sq == err_sq)) pow_term = err_sq;              // NaN stays NaN (fmin / fmax below drop it)
+                if (err_sq > 5.0) {                                      // err_norm > 1: reject, metrics.py:516-522
                     const double factor = fmax(0.2, pow_term);
                     h *= factor;
                     if (h < h_min) done = 2;
@@ -445,7 +448,7 @@ __device__ __forceinline__ void kerr_trip(double (&state)[5], double (&k1)[5], d
                         lam += h;
                         if (!finite5(state)) {
                             done = 2;
-                        } else if (err_norm < 1e-10) {
+                        } else if (e2 < 1e-20) {                        // err_norm < 1e-10
                             h *= 5.0;
                         } else {
                             h *= fmin(5.0, pow_term);

@@ -79,7 +79,7 @@ struct Rk45Args {
     double *dense;              // optional [n][max_points][25]: row k >= 1 = (h, Q[6][4]) of the accepted step
                                 // that ended in point k — scipy's RkDenseOutput (rk.py:178-180, :715-737)
     int32_t refill_min;         // lanes that must be waiting before a flush (RK_REFILL_MIN)
-    int32_t fast_pow;           // step controller: err^-0.2 as exp2(-0.2 log2 err) instead of pow()
+    int32_t fast_pow;           // step controller: 0.9 err^-0.2 by inv_tenth_root on the squared norm instead of pow()
 };
 
 struct ThetaCache { double th, s, c; };
@@ -473,12 +473,15 @@ lp_rk45_kernel(const Rk45Args a)
                     esum = fma(e, e, esum);
                 }
             }
-            const double error_norm = rms8(esum);
-            // one pow for the accept and the reject controller (rk.py:155-170): divergent branches
+            // one power for the accept and the reject controller (rk.py:155-170): divergent branches
             // would each run their own copy for the whole warp
-            // (fast_pow: x^-0.2 = exp2(-0.2 log2 x), a few ulp — the level at which scipy's own BLAS stage
-            // sums already differ from any restatement; tests hold the accept/reject sequences identical)
-            const double pow_term = 0.9 * (a.fast_pow ? exp2(-0.2 * log2(error_norm)) : pow(error_norm, -0.2));
+            // (fast_pow: the controller on the SQUARED norm, 0.9 err^-0.2 = 0.9 (esum / 8)^-0.1 by
+            // inv_tenth_root — a few ulp, the level at which scipy's own BLAS stage sums already differ
+            // from any restatement; error_norm is then only compared with 0 and 1, which the square
+            // preserves; tests hold the accept/reject sequences identical)
+            double error_norm, pow_term;
+            if (a.fast_pow) { error_norm = esum * 0.125; pow_term = 0.9 * inv_tenth_root(error_norm); }
+            else { error_norm = rms8(esum); pow_term = 0.9 * pow(error_norm, -0.2); }
             if (error_norm < 1) {
                 double factor = (error_norm == 0) ? 10.0 : fmin(10.0, pow_term);
                 if (rejected) factor = fmin(1.0, factor);
@@ -787,8 +790,9 @@ lp_rk45_eq_kernel(const Rk45Args a)
                     esum = fma(e, e, esum);
                 }
             }
-            const double error_norm = rms8(esum);
-            const double pow_term = 0.9 * (a.fast_pow ? exp2(-0.2 * log2(error_norm)) : pow(error_norm, -0.2));
+            double error_norm, pow_term;                 // see lp_rk45_kernel
+            if (a.fast_pow) { error_norm = esum * 0.125; pow_term = 0.9 * inv_tenth_root(error_norm); }
+            else { error_norm = rms8(esum); pow_term = 0.9 * pow(error_norm, -0.2); }
             if (error_norm < 1) {
                 double factor = (error_norm == 0) ? 10.0 : fmin(10.0, pow_term);
                 if (rejected) factor = fmin(1.0, factor);
@@ -939,7 +943,7 @@ static int rk45_launch(bool metric_is_kerr, double kerr_a, const double *alphas,
         refill = (v >= 1 && v <= 32) ? v : RK_REFILL_MIN;
     }
     a.refill_min = refill;
-    // LP_RK45_POW = 0 | 1: pow() or exp2(-0.2 log2 x) in the step controller (tuning knob)
+    // LP_RK45_POW = 0 | 1: pow() or inv_tenth_root() of the squared norm in the step controller (tuning knob)
     // default: on in the equatorial batch kernel (4K frame 94 -> 86 ms), off in the six-component kernel of
     // the single-ray API, whose fixtures were pinned with pow()
     static int fast_pow = -2;
