@@ -117,19 +117,21 @@ __device__ __forceinline__ void rk_rhs(double R_S, double r_floor, double p_t, d
     // any restatement, and it removes most of the FP64-pipe work of an evaluation (an IEEE
     // division is ~12 dependent pipe slots); tests/test_gpu_rk45.py holds the result to the same
     // bar (identical accept/reject sequences, final state <= 1e-9).
+    // (sums contracted into fma: 18 FP64 instructions on the equator instead of 24 — the rounding differs from the
+    // separately rounded form at the level the reciprocals already do)
     const double ir = fast_rcp(r);
     const double ir2 = ir * ir, ir3 = ir2 * ir;
-    const double f = 1.0 - R_S * ir;
+    const double f = fma(-R_S, ir, 1.0);
     const double inv_f = fast_rcp(f);
     double is2 = 1.0, is1 = tc.s;                          // equatorial plane: sin(theta) = +-1 exactly
     if (s2 != 1.0) { is2 = fast_rcp(s2); is1 = fast_rcp(tc.s); }
-    const double a = 0.5 * R_S * ir2;
+    const double a = (0.5 * R_S) * ir2;
     const double ptf = p_t * inv_f;
     d[0] = -ptf;
     d[1] = f * p_r;
     d[2] = p_th * ir2;
     d[3] = p_phi * ir2 * is2;
-    d[4] = (-a * (ptf * ptf) - a * (p_r * p_r)) + ((p_th * p_th) + pp2 * is2) * ir3;
+    d[4] = fma(-a, fma(ptf, ptf, p_r * p_r), fma(pp2, is2, p_th * p_th) * ir3);
     d[5] = tc.c * pp2 * ir2 * is2 * is1;
 #endif
 }
@@ -462,7 +464,7 @@ lp_rk45_kernel(const Rk45Args a)
             }
 #pragma unroll
             for (int i = 0; i < RK_NC; ++i) {
-                const double e = div_by(en[i], es[i], div_rcp(es[i]));
+                const double e = en[i] * fast_rcp(es[i]);        // es >= atol > 0; only the controller sees it
                 esum = fma(e, e, esum);
             }
             if (!isfinite(esum)) {
@@ -589,11 +591,17 @@ lp_rk45_kernel(const Rk45Args a)
 // ---------------------------------------------------------------------------------------------
 #define RK_EQ 4
 
+// SPEC: no test inside — the caller collects `below |= r <= r_floor` (one predicate instruction per
+// evaluation) and repeats the step attempt with the tested form in the rare case that a stage did land
+// below the floor (the test, its branch and the zero defaults cost ~10 issue slots per evaluation).
+template <bool SPEC>
 __device__ __forceinline__ void rk_rhs_eq(double R_S, double r_floor, double p_t, double p_phi, double pp2,
-                                          const double (&y)[RK_EQ], double (&d)[RK_EQ])
+                                          const double (&y)[RK_EQ], double (&d)[RK_EQ], bool &below)
 {
     const double r = y[1], p_r = y[3];
-    if (r <= r_floor) {                                   // metrics.py:766-767
+    if (SPEC) {
+        below = below || (r <= r_floor);
+    } else if (r <= r_floor) {                            // metrics.py:766-767
 #pragma unroll
         for (int i = 0; i < RK_EQ; ++i) d[i] = 0.0;
         return;
@@ -601,14 +609,44 @@ __device__ __forceinline__ void rk_rhs_eq(double R_S, double r_floor, double p_t
     // rk_rhs with sin(theta) = 1, p_theta = 0: the same operations on the same operands
     const double ir = fast_rcp(r);
     const double ir2 = ir * ir, ir3 = ir2 * ir;
-    const double f = 1.0 - R_S * ir;
+    const double f = fma(-R_S, ir, 1.0);
     const double inv_f = fast_rcp(f);
-    const double a = 0.5 * R_S * ir2;
+    const double a = (0.5 * R_S) * ir2;
     const double ptf = p_t * inv_f;
     d[0] = -ptf;
     d[1] = f * p_r;
     d[2] = p_phi * ir2;
-    d[3] = (-a * (ptf * ptf) - a * (p_r * p_r)) + pp2 * ir3;
+    d[3] = fma(-a, fma(ptf, ptf, p_r * p_r), pp2 * ir3);
+}
+
+// The six stages of one step attempt (rk.py:111-176 / rk_step): K[0] = f on entry; K[1..6] and y_new on exit.
+template <bool SPEC>
+__device__ __forceinline__ void rk_eq_stages(double R_S, double r_floor, double p_t, double p_phi, double pp2, double h,
+                                             const double (&y)[RK_EQ], double (&K)[7][RK_EQ], double (&y_new)[RK_EQ],
+                                             bool &below)
+{
+#pragma unroll
+    for (int s = 1; s < 6; ++s) {
+        double ys[RK_EQ];
+#pragma unroll
+        for (int i = 0; i < RK_EQ; ++i) {
+            double dy = K[0][i] * c_A[s][0];
+#pragma unroll
+            for (int j = 1; j < s; ++j) dy = fma(K[j][i], c_A[s][j], dy);
+            ys[i] = fma(dy, h, y[i]);
+        }
+        rk_rhs_eq<SPEC>(R_S, r_floor, p_t, p_phi, pp2, ys, K[s], below);
+    }
+#pragma unroll
+    for (int i = 0; i < RK_EQ; ++i) {
+        double acc = K[0][i] * c_B[0];
+        acc = fma(K[2][i], c_B[2], acc);
+        acc = fma(K[3][i], c_B[3], acc);
+        acc = fma(K[4][i], c_B[4], acc);
+        acc = fma(K[5][i], c_B[5], acc);
+        y_new[i] = fma(h, acc, y[i]);
+    }
+    rk_rhs_eq<SPEC>(R_S, r_floor, p_t, p_phi, pp2, y_new, K[6], below);
 }
 
 template <int MINB>
@@ -742,29 +780,10 @@ lp_rk45_eq_kernel(const Rk45Args a)
             double K[7][RK_EQ];
 #pragma unroll
             for (int i = 0; i < RK_EQ; ++i) K[0][i] = f[i];
-#pragma unroll
-            for (int s = 1; s < 6; ++s) {
-                double ys[RK_EQ];
-#pragma unroll
-                for (int i = 0; i < RK_EQ; ++i) {
-                    double dy = K[0][i] * c_A[s][0];
-#pragma unroll
-                    for (int j = 1; j < s; ++j) dy = fma(K[j][i], c_A[s][j], dy);
-                    ys[i] = fma(dy, h, y[i]);
-                }
-                rk_rhs_eq(a.R_S, r_floor, p_t, p_phi, pp2, ys, K[s]);
-            }
             double y_new[RK_EQ];
-#pragma unroll
-            for (int i = 0; i < RK_EQ; ++i) {
-                double acc = K[0][i] * c_B[0];
-                acc = fma(K[2][i], c_B[2], acc);
-                acc = fma(K[3][i], c_B[3], acc);
-                acc = fma(K[4][i], c_B[4], acc);
-                acc = fma(K[5][i], c_B[5], acc);
-                y_new[i] = fma(h, acc, y[i]);
-            }
-            rk_rhs_eq(a.R_S, r_floor, p_t, p_phi, pp2, y_new, K[6]);
+            bool below = false;
+            rk_eq_stages<true>(a.R_S, r_floor, p_t, p_phi, pp2, h, y, K, y_new, below);
+            if (below) rk_eq_stages<false>(a.R_S, r_floor, p_t, p_phi, pp2, h, y, K, y_new, below);   // cold
             double esum = 0.0, en[RK_EQ], es[RK_EQ];
 #pragma unroll
             for (int i = 0; i < RK_EQ; ++i) {
@@ -779,7 +798,7 @@ lp_rk45_eq_kernel(const Rk45Args a)
             }
 #pragma unroll
             for (int i = 0; i < RK_EQ; ++i) {
-                const double e = div_by(en[i], es[i], div_rcp(es[i]));
+                const double e = en[i] * fast_rcp(es[i]);        // es >= atol > 0; only the controller sees it
                 esum = fma(e, e, esum);
             }
             if (!isfinite(esum)) {
