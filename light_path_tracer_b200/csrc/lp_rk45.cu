@@ -237,6 +237,12 @@ __device__ __noinline__ double rk_brentq(const double (&q)[4], double h, double 
     return xcur;
 }
 
+// max / min as one compare and a select (fmax / fmin expand to ~7 instructions on sm_100: no DMNMX).  A NaN in
+// the SECOND operand is returned, a NaN in the first is dropped; the call sites below only ever see a NaN
+// where the result is discarded or where that is the reference's behaviour (max(MIN_FACTOR, nan)).
+__device__ __forceinline__ double max_sel(double a, double b) { return (a > b) ? a : b; }
+__device__ __forceinline__ double min_sel(double a, double b) { return (a < b) ? a : b; }
+
 __device__ __forceinline__ double rms8(double sumsq)     // common.py:63-65 with x.size == 8
 {
     return __dsqrt_rn(sumsq) / 2.8284271247461903;       // 8 ** 0.5
@@ -453,7 +459,7 @@ lp_rk45_kernel(const Rk45Args a)
             double esum = 0.0, en[RK_NC], es[RK_NC];
 #pragma unroll
             for (int i = 0; i < RK_NC; ++i) {
-                es[i] = atol + fmax(fabs(y[i]), fabs(y_new[i])) * rtol;
+                es[i] = atol + max_sel(fabs(y[i]), fabs(y_new[i])) * rtol;
                 double acc = K[0][i] * c_E[0];
                 acc = fma(KGET(2, i), c_E[2], acc);
                 acc = fma(KGET(3, i), c_E[3], acc);
@@ -485,8 +491,8 @@ lp_rk45_kernel(const Rk45Args a)
             if (a.fast_pow) { error_norm = esum * 0.125; pow_term = 0.9 * inv_tenth_root(error_norm); }
             else { error_norm = rms8(esum); pow_term = 0.9 * pow(error_norm, -0.2); }
             if (error_norm < 1) {
-                double factor = (error_norm == 0) ? 10.0 : fmin(10.0, pow_term);
-                if (rejected) factor = fmin(1.0, factor);
+                double factor = (error_norm == 0) ? 10.0 : min_sel(pow_term, 10.0);
+                if (rejected) factor = min_sel(factor, 1.0);
                 ha *= factor;
                 // ---- accepted: events on the new point (ivp.py:676-699) ----
                 const double gn0 = y_new[1] - a.r_in, gn1 = y_new[1] - r_out;
@@ -551,7 +557,7 @@ lp_rk45_kernel(const Rk45Args a)
                 for (int i = 0; i < RK_NC; ++i) { y[i] = y_new[i]; f[i] = K[6][i]; }
                 fresh = true;
             } else {
-                ha *= fmax(0.2, pow_term);
+                ha *= max_sel(pow_term, 0.2);
                 rejected = true;
             }
         }
@@ -591,16 +597,17 @@ lp_rk45_kernel(const Rk45Args a)
 // ---------------------------------------------------------------------------------------------
 #define RK_EQ 4
 
-// SPEC: no test inside — the caller collects `below |= r <= r_floor` (one predicate instruction per
-// evaluation) and repeats the step attempt with the tested form in the rare case that a stage did land
-// below the floor (the test, its branch and the zero defaults cost ~10 issue slots per evaluation).
+// SPEC: no test inside — the caller collects the smallest high word of r over the evaluations of a step
+// attempt (one integer min each; a negative r is a negative word, a NaN a large one, as in the fp64 test)
+// and repeats the attempt with the tested form in the rare case that a stage may have landed at or below
+// the floor (the test, its branch and the zero defaults cost ~10 issue slots per evaluation).
 template <bool SPEC>
 __device__ __forceinline__ void rk_rhs_eq(double R_S, double r_floor, double p_t, double p_phi, double pp2,
-                                          const double (&y)[RK_EQ], double (&d)[RK_EQ], bool &below)
+                                          const double (&y)[RK_EQ], double (&d)[RK_EQ], int &r_hi_min)
 {
     const double r = y[1], p_r = y[3];
     if (SPEC) {
-        below = below || (r <= r_floor);
+        r_hi_min = min(r_hi_min, __double2hiint(r));
     } else if (r <= r_floor) {                            // metrics.py:766-767
 #pragma unroll
         for (int i = 0; i < RK_EQ; ++i) d[i] = 0.0;
@@ -623,7 +630,7 @@ __device__ __forceinline__ void rk_rhs_eq(double R_S, double r_floor, double p_t
 template <bool SPEC>
 __device__ __forceinline__ void rk_eq_stages(double R_S, double r_floor, double p_t, double p_phi, double pp2, double h,
                                              const double (&y)[RK_EQ], double (&K)[7][RK_EQ], double (&y_new)[RK_EQ],
-                                             bool &below)
+                                             int &r_hi_min)
 {
 #pragma unroll
     for (int s = 1; s < 6; ++s) {
@@ -635,7 +642,7 @@ __device__ __forceinline__ void rk_eq_stages(double R_S, double r_floor, double 
             for (int j = 1; j < s; ++j) dy = fma(K[j][i], c_A[s][j], dy);
             ys[i] = fma(dy, h, y[i]);
         }
-        rk_rhs_eq<SPEC>(R_S, r_floor, p_t, p_phi, pp2, ys, K[s], below);
+        rk_rhs_eq<SPEC>(R_S, r_floor, p_t, p_phi, pp2, ys, K[s], r_hi_min);
     }
 #pragma unroll
     for (int i = 0; i < RK_EQ; ++i) {
@@ -646,7 +653,7 @@ __device__ __forceinline__ void rk_eq_stages(double R_S, double r_floor, double 
         acc = fma(K[5][i], c_B[5], acc);
         y_new[i] = fma(h, acc, y[i]);
     }
-    rk_rhs_eq<SPEC>(R_S, r_floor, p_t, p_phi, pp2, y_new, K[6], below);
+    rk_rhs_eq<SPEC>(R_S, r_floor, p_t, p_phi, pp2, y_new, K[6], r_hi_min);
 }
 
 template <int MINB>
@@ -781,13 +788,14 @@ lp_rk45_eq_kernel(const Rk45Args a)
 #pragma unroll
             for (int i = 0; i < RK_EQ; ++i) K[0][i] = f[i];
             double y_new[RK_EQ];
-            bool below = false;
-            rk_eq_stages<true>(a.R_S, r_floor, p_t, p_phi, pp2, h, y, K, y_new, below);
-            if (below) rk_eq_stages<false>(a.R_S, r_floor, p_t, p_phi, pp2, h, y, K, y_new, below);   // cold
+            int r_hi_min = 0x7fffffff;
+            rk_eq_stages<true>(a.R_S, r_floor, p_t, p_phi, pp2, h, y, K, y_new, r_hi_min);
+            // a stage at or (by less than one high word) above the floor: the tested form decides — cold
+            if (r_hi_min <= __double2hiint(r_floor)) rk_eq_stages<false>(a.R_S, r_floor, p_t, p_phi, pp2, h, y, K, y_new, r_hi_min);
             double esum = 0.0, en[RK_EQ], es[RK_EQ];
 #pragma unroll
             for (int i = 0; i < RK_EQ; ++i) {
-                es[i] = atol + fmax(fabs(y[i]), fabs(y_new[i])) * rtol;
+                es[i] = atol + max_sel(fabs(y[i]), fabs(y_new[i])) * rtol;
                 double acc = K[0][i] * c_E[0];
                 acc = fma(K[2][i], c_E[2], acc);
                 acc = fma(K[3][i], c_E[3], acc);
@@ -813,8 +821,8 @@ lp_rk45_eq_kernel(const Rk45Args a)
             if (a.fast_pow) { error_norm = esum * 0.125; pow_term = 0.9 * inv_tenth_root(error_norm); }
             else { error_norm = rms8(esum); pow_term = 0.9 * pow(error_norm, -0.2); }
             if (error_norm < 1) {
-                double factor = (error_norm == 0) ? 10.0 : fmin(10.0, pow_term);
-                if (rejected) factor = fmin(1.0, factor);
+                double factor = (error_norm == 0) ? 10.0 : min_sel(pow_term, 10.0);
+                if (rejected) factor = min_sel(factor, 1.0);
                 ha *= factor;
                 const double gn0 = y_new[1] - a.r_in, gn1 = y_new[1] - r_out;
                 const bool act0 = (g0 >= 0) && (gn0 <= 0);
@@ -861,7 +869,7 @@ lp_rk45_eq_kernel(const Rk45Args a)
                 for (int i = 0; i < RK_EQ; ++i) { y[i] = y_new[i]; f[i] = K[6][i]; }
                 fresh = true;
             } else {
-                ha *= fmax(0.2, pow_term);
+                ha *= max_sel(pow_term, 0.2);
                 rejected = true;
             }
         }
