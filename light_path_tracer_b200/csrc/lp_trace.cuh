@@ -53,7 +53,7 @@ __device__ __forceinline__ int tile_row(const TraceArgs &a, int r)
 // thread index -> tile-local (row r, column) under the warp-tile mapping
 __device__ __forceinline__ void warp_tile_rc(const TraceArgs &a, int width, long long i, int &r, int &col)
 {
-    if (a.tile_h <= 1) { pixel_row_col(i, a.n, width, 0, r, col); return; }
+    if (a.tile_h <= 1 && !a.tiles_x_magic) { pixel_row_col(i, a.n, width, 0, r, col); return; }   // (32 x 1 tiles of a width that is a multiple of 32 take the multiply-high path)
     const unsigned wi = (unsigned)(i >> 5), l = (unsigned)i & 31u;
     const unsigned tw_shift = 5u - a.tile_shift;
     const unsigned ty = a.tiles_x_magic ? __umulhi(wi, a.tiles_x_magic) : wi / (unsigned)a.tiles_x;
