@@ -204,7 +204,7 @@ def workload_config(n, H, W, gather_mode="peer", band_rows=None):
             "image_format": "uint8 RGB in / uint8 RGB out (LP_DTYPE_U8_UNIT); float32 frames beside it in "
                             "`float32_frames` (N = 1) / `weak_f32_frames` (N > 1)",
             "arithmetic": "hybrid (LP_TRACE_HYBRID, the image pipeline's default): FMA-contracted RK4 loop, strict "
-                          "re-trace of rays longer than 240 steps; same classification / winding / float32 "
+                          "re-trace of the few rays that sweep more than 11.5 + ln max(final_alpha, 1e-3) rad inside r < 6M; same classification / winding / float32 "
                           "final_alpha as the strict kernel on this frame (tests/test_gpu_frame.py)",
             "l2": "256 MiB buffer written between timed steps (L2 flush)"}
 

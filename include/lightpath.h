@@ -53,10 +53,10 @@ extern "C" {
                                      one-ray-per-thread kernel on every frame tried, including the
                                      divergent ones (profiles/r2b_repack_perf_refill_sweep.log) — the
                                      default keeps divergence down with 8x4-pixel warp tiles instead */
-#define LP_TRACE_HYBRID     4u    /* FMA-contracted loop for rays that finish within 12 rad
-                                     of swept angle (240 RK4 steps at h = 0.05; they stay
-                                     within 1e-11 of the strict result), strict re-trace of
-                                     the few longer ones
+#define LP_TRACE_HYBRID     4u    /* FMA-contracted loop for rays that sweep at most
+                                     11.5 + ln max(final_alpha, 1e-3) rad inside r < 6M
+                                     (where rounding differences can grow: csrc/lp_trace.cu),
+                                     strict re-trace of the few longer ones
                                      (near-critical rays, where rounding differences are
                                      amplified): same classification and winding as
                                      LP_TRACE_STRICT, final_alpha within 1e-9 relative  */

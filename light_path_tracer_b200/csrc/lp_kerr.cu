@@ -74,8 +74,12 @@ __device__ __noinline__ K5 kerr_rhs_regs(double r, double th, double p_r, double
         out.v0 = out.v1 = out.v2 = out.v3 = out.v4 = 0.0;
         return out;
     }
+    // theta is a polar angle (a few pi at most): the straight-line sincos of lp_internal.cuh (fdlibm kernel
+    // polynomials, constants from the constant bank) instead of the library call with its immediates and
+    // slow-path branch — either differs from the host's libm in the last place, which the Kerr bar allows for
     double sin_th, cos_th;
-    sincos(th, &sin_th, &cos_th);
+    if (fabs(th) < 1.0e4) sincos_moderate(th, sin_th, cos_th);
+    else sincos(th, &sin_th, &cos_th);
     double sin_th_sq = sin_th * sin_th;
     if (sin_th_sq < 1e-15) sin_th_sq = 1e-15;
     if (EXACT) {

@@ -55,7 +55,7 @@ struct RpQueues {
 template <bool FUSED>
 __device__ __forceinline__ void rp_finish_ray(const BinetConsts &c, const LoopRegs &L, int code, int k,
                                               double up, double wp, double u, double w, double alpha,
-                                              int retrace_steps, RayResult &r)
+                                              int retrace_steps, int retrace_steps_small, float retrace_h, float retrace_off, RayResult &r)
 {
     if (code == RP_INVALID) {
         r.status = 0; r.nh = 0; r.steps = 0; r.fa = __longlong_as_double(0x7ff8000000000000LL);
@@ -99,7 +99,8 @@ __device__ __forceinline__ void rp_finish_ray(const BinetConsts &c, const LoopRe
         binet_cross_s<FUSED>(c, cap, L.h, binet_phi_at<FUSED>(c, k), up, wp, u, w, phi);
     }
     binet_finish<FUSED>(c, status, phi, u, w, r);
-    if (FUSED && r.steps > retrace_steps) binet_trace<false, true>(c, load_loop_regs<false>(c), alpha, r);     // LP_TRACE_HYBRID
+    if (FUSED && hybrid_needs_retrace(r, retrace_steps, retrace_steps_small, retrace_h, retrace_off))
+        binet_trace<false, true>(c, load_loop_regs<false>(c), alpha, r);     // LP_TRACE_HYBRID
 }
 
 // per-warp frame statistics (shared memory; filled by warp reductions in the finish phase so that
@@ -167,7 +168,7 @@ lp_render_repack_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts
                 const int p = q.out_pix[e];
                 const float al = q.out_a32[e];
                 rp_finish_ray<FUSED>(c, L, q.out_code[e], q.out_k[e], q.out_up[e], q.out_wp[e], q.out_u[e], q.out_w[e],
-                                     (double)al, a.retrace_steps, r);
+                                     (double)al, a.retrace_steps, a.retrace_steps_small, a.retrace_h, a.retrace_off, r);
                 const long long i = chunk0 + p;
                 int row, col;
                 long long oi;

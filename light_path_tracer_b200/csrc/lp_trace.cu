@@ -16,23 +16,66 @@
 #define LP_RENDER_DEFAULT_SPAN 2
 #define LP_TRACE_DEFAULT_BLOCK 64   /* rays per CTA; LP_TRACE_BLOCK=32|64|128|256 overrides (tuning) */
 
-// LP_TRACE_HYBRID threshold.  The FMA-contracted loop differs from the strict one by ~1e-16
-// per operation; the difference grows like e^phi while a ray lingers at the photon sphere.
-// Measured (tools/fma_study.c, 2.4e7 rays over r_obs = 15..1000, dense around alpha_crit):
-// rays that finish within 275 steps agree with the strict loop to <= 3e-11 relative in
-// final_alpha with identical status and n_half_orbits; 240 (phi <= 12, <= 6e-12) leaves two
-// orders of margin to the 1e-9 parity bound, and in a 4K frame only ~1e-4 of the rays are
-// longer than that (they are the ones the strict retrace exists for).
-// (what matters is the swept angle, 240 steps x 0.05 rad = 12 rad: for another step size the
-// threshold is the number of steps that sweeps the same angle)
-#define LP_HYBRID_RETRACE_PHI 12.0
+// LP_TRACE_HYBRID rule.  The FMA loop (scaled second-order form, lp_internal.cuh) differs from the strict one
+// by ~1e-16 per operation.  A perturbation d of the orbit obeys d'' = (-1 + 6 M u) d: it can only grow where
+// r < 6M, at a rate <= 1 per radian for r >= 3M (= 1 at the photon sphere; an escaping ray never goes below 3M),
+// so the difference is amplified by at most e^(phi - phi_out), phi_out = the angle the ray sweeps outside 6M.
+// phi_out is smallest for the critical impact parameter, where it has a closed integrand
+//     phi_out >= I(1/r_obs) + I(1/(2 r_obs)),  I(u0) = int_{u0}^{1/6M} du / sqrt(1/(27 M^2) - u^2 + 2 M u^3)
+// (way in from the observer, way out to the escape radius; 1.87 rad at r_obs = 100 M, 0.16 at 3.49 M).
+// The parity bar is |d final_alpha| <= 1e-9 max(final_alpha, 1e-3), so with ~1e-15 accumulated per ray and a
+// factor ten of margin a ray may keep its FMA result while
+//     e^(phi - phi_out) <= 1e5 max(final_alpha, 1e-3),   i.e.   phi - phi_out <= 11.5 + ln max(final_alpha, 1e-3):
+// nobody is re-traced below phi - phi_out = 4.6, everybody above 11.5, and in between the rays whose
+// final_alpha is small — the thin Einstein rings.  Re-traced rays are traced again strictly by the same thread
+// (its warp waits: a re-traced ray costs about three warps' worth of time, which is why the rule is not simply
+// "everything above 4.6 rad").  Measured: tools/nystrom_study.c (rays of <= 249 steps agree to a few 1e-11 over
+// r_obs = 3.5 .. 1000 — relative to final_alpha >= 1e-3, which is what the final_alpha term is for:
+// tools/parity_fuzz.py seed 31 found a 1.08e-12 difference at final_alpha = 9e-4, r_obs = 3.49 M, under the
+// single 12-rad threshold this replaces).
+#define LP_HYBRID_RETRACE_PHI 11.5
+#define LP_HYBRID_RETRACE_PHI_SMALL 4.6
 
-int lp_retrace_steps_for(uint32_t flags, double h_max)
+static double hybrid_phi_outside(double M, double r_obs)
 {
-    if (!(flags & LP_TRACE_HYBRID)) return 0x7fffffff;
+    if (!(M > 0.0) || !(r_obs > 0.0) || !isfinite(M) || !isfinite(r_obs)) return 0.0;
+    const double u6 = 1.0 / (6.0 * M), c0 = 1.0 / (27.0 * M * M);
+    double total = 0.0;
+    for (int leg = 0; leg < 2; ++leg) {
+        const double u0 = 1.0 / (leg == 0 ? r_obs : 2.0 * r_obs);
+        if (!(u0 < u6)) continue;
+        const int n = 2000;                              // Simpson; the integrand is smooth below the double root at 1/3M
+        const double hq = (u6 - u0) / n;
+        double acc = 0.0;
+        for (int i = 0; i <= n; ++i) {
+            const double u = u0 + hq * i;
+            const double f = 1.0 / sqrt(c0 - u * u + 2.0 * M * u * u * u);
+            acc += f * ((i == 0 || i == n) ? 1.0 : (i & 1) ? 4.0 : 2.0);
+        }
+        total += acc * hq / 3.0;
+    }
+    return (total > 0.0 && isfinite(total)) ? total : 0.0;
+}
+
+static int steps_for_phi(double phi, double h_max)
+{
     if (!(h_max > 0.0)) return 0;                       // degenerate step: everything strict
-    const double k = floor(LP_HYBRID_RETRACE_PHI / h_max + 1e-9);
+    const double k = floor(phi / h_max + 1e-9);
     return k < 1.0 ? 0 : (k > 1.0e9 ? 0x7fffffff : (int)k);
+}
+
+void lp_hybrid_rule(uint32_t flags, double M, double r_obs, double h_max, TraceArgs *a)
+{
+    a->retrace_steps = a->retrace_steps_small = 0x7fffffff;
+    a->retrace_h = (float)h_max; a->retrace_off = 0.0f;
+    if (!(flags & LP_TRACE_HYBRID)) return;
+    // (the quadrature is ~20 us of host time: remembered per thread for the last configuration)
+    static thread_local double last_M = 0.0, last_r = 0.0, last_phi = 0.0;
+    if (!(M == last_M && r_obs == last_r)) { last_phi = hybrid_phi_outside(M, r_obs); last_M = M; last_r = r_obs; }
+    const double phi_out = 0.95 * last_phi;              // (5 % off the bound for the quadrature and the float test)
+    a->retrace_steps = steps_for_phi(LP_HYBRID_RETRACE_PHI + phi_out, h_max);
+    a->retrace_steps_small = steps_for_phi(LP_HYBRID_RETRACE_PHI_SMALL + phi_out, h_max);
+    a->retrace_off = (float)(LP_HYBRID_RETRACE_PHI + phi_out);
 }
 
 // One ray per thread, one CTA per `blockDim.x` consecutive rays.  The grid is NOT
@@ -65,7 +108,8 @@ lp_trace_kernel(const TraceArgs a, const BinetConsts c, const CamConsts cam)
             alpha = (double)a32;
         }
         binet_trace<FUSED, FAST, (FUSED && FAST) ? LP_RENDER_DEFAULT_TRIP : 2>(c, L, alpha, r);
-        if (FUSED && r.steps > a.retrace_steps) binet_trace<false, FAST>(c, load_loop_regs<false>(c), alpha, r);   // cold: its own constants
+        if (__builtin_expect(FUSED && hybrid_needs_retrace(r, a.retrace_steps, a.retrace_steps_small, a.retrace_h, a.retrace_off), 0))
+            binet_trace<false, FAST>(c, load_loop_regs<false>(c), alpha, r);   // cold: its own constants
         const double fa = (r.status == 1) ? r.fa : __longlong_as_double(0x7ff8000000000000LL);
         if (WIDE) {
             ((double *)a.out_fa)[i] = fa;                          // metrics.py:667
@@ -134,7 +178,7 @@ extern "C" int lp_schw_trace_batch_f64(const double *alphas, int64_t n,
     if (rc != LP_OK) return rc;
     CamConsts cam = {};
     TraceArgs a = {};
-    a.retrace_steps = lp_retrace_steps_for(flags, h_max);
+    lp_hybrid_rule(flags, M, r_obs, h_max, &a);
     a.alphas = alphas; a.n = n; a.out_fa = out_fa; a.out_w = out_w;
     a.out_status = out_status; a.out_steps = out_steps; a.stats = stats;
     return launch_trace<SRC_F64, true>(a, c, cam, flags, (cudaStream_t)stream);
@@ -154,7 +198,7 @@ extern "C" int lp_schw_trace_alpha32(const float *alpha32, int64_t n,
     if (rc != LP_OK) return rc;
     CamConsts cam = {};
     TraceArgs a = {};
-    a.retrace_steps = lp_retrace_steps_for(flags, h_max);
+    lp_hybrid_rule(flags, M, r_obs, h_max, &a);
     a.alphas = alpha32; a.n = n; a.out_fa = out_fa32; a.out_w = out_w16;
     a.out_status = out_status; a.out_steps = out_steps; a.stats = stats;
     return launch_trace<SRC_F32, false>(a, c, cam, flags, (cudaStream_t)stream);
@@ -177,7 +221,7 @@ extern "C" int lp_schw_trace_frame(const lp_camera *h_cam, int32_t row0, int32_t
     rc = lp_make_binet_consts(M, R_S, r_obs, phi_max, h_max, &c);
     if (rc != LP_OK) return rc;
     TraceArgs a = {};
-    a.retrace_steps = lp_retrace_steps_for(flags, h_max);
+    lp_hybrid_rule(flags, M, r_obs, h_max, &a);
     a.n = n; a.out_fa = out_fa32; a.out_w = out_w16; a.out_alpha32 = out_alpha32;
     a.out_status = out_status; a.out_steps = out_steps; a.stats = stats; a.row0 = row0;
     return launch_trace<SRC_CAM, false>(a, c, cam, flags, (cudaStream_t)stream);
@@ -279,7 +323,8 @@ lp_render_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts c, con
             const double xc = cam_x(cam, col), yc = cam_y(cam, row);     // also the remap's (kept across the loop)
             const float a32 = (float)pixel_alpha64(cam, xc, yc);
             binet_trace<FUSED, FAST, TRIP>(c, L, (double)a32, r);
-            if (FUSED && r.steps > a.retrace_steps) binet_trace<false, FAST>(c, load_loop_regs<false>(c), (double)a32, r);   // cold
+            if (FUSED && hybrid_needs_retrace(r, a.retrace_steps, a.retrace_steps_small, a.retrace_h, a.retrace_off))
+                binet_trace<false, FAST>(c, load_loop_regs<false>(c), (double)a32, r);   // cold
             const float fa32 = (float)((r.status == 1) ? r.fa : __longlong_as_double(0x7ff8000000000000LL));
             const long long nh = r.nh < 0 ? 0 : (r.nh > 65535 ? 65535 : r.nh);
             if (a.out_fa) ((float *)a.out_fa)[pi] = fa32;
@@ -446,7 +491,7 @@ extern "C" int lp_render_frame_bands(const void *src, int32_t src_dtype, int32_t
     if (rc != LP_OK) return rc;
     const bool frame_rows = (flags & LP_RENDER_OUT_FRAME_ROWS) != 0;
     TraceArgs a = {};
-    a.retrace_steps = lp_retrace_steps_for(flags, h_max);
+    lp_hybrid_rule(flags, M, r_obs, h_max, &a);
     a.n = n; a.out_fa = out_fa32; a.out_w = out_w16; a.stats = stats; a.row0 = row0;
     a.band_rows = band_rows; a.band_stride = band_stride;
     a.out_frame_rows = (frame_rows && band_rows > 0) ? 1 : 0;     // contiguous rows: frame-addressed == compact

@@ -18,6 +18,8 @@ struct TraceArgs {
     int32_t *out_steps;     // optional
     lp_frame_stats *stats;  // optional
     int32_t row0;           // SRC_CAM: first frame row of the tile
+    int32_t retrace_steps_small;   // ... and the step count below which no ray is (see hybrid_needs_retrace)
+    float retrace_h, retrace_off;  // step size and exponent offset as floats, for that test
     int32_t retrace_steps;  // FUSED kernels: a ray that ran more RK4 steps than this is traced
                             // again with strict arithmetic (LP_TRACE_HYBRID); INT_MAX = never
     // interleaved row bands (lp_render_frame_bands): tile-local row r is frame row
@@ -76,6 +78,20 @@ __device__ __forceinline__ void tile_pixel(const TraceArgs &a, int width, long l
     oi = a.out_frame_rows ? (long long)r * width + col : i;
 }
 
-int lp_retrace_steps_for(uint32_t flags, double h_max);
+// LP_TRACE_HYBRID (lp_trace.cu): fills retrace_steps, retrace_steps_small, retrace_h, retrace_off of `a`
+void lp_hybrid_rule(uint32_t flags, double M, double r_obs, double h_max, TraceArgs *a);
+
+// Does the FMA loop's result have to be replaced by a strict re-trace?  With phi = steps * h:
+//   steps > retrace_steps                                     (phi - phi_out > 11.5), or
+//   steps > retrace_steps_small (phi - phi_out > 4.6) and max(final_alpha, 1e-3) < exp(phi - retrace_off)
+// where retrace_off = 11.5 + phi_out and phi_out is the part of the swept angle that cannot amplify (lp_trace.cu).
+__device__ __forceinline__ bool hybrid_needs_retrace(const RayResult &r, int retrace_steps, int retrace_steps_small,
+                                                     float h, float off)
+{
+    if (r.steps <= retrace_steps_small) return false;                 // 99.9 % of a frame's rays stop here
+    if (r.steps > retrace_steps) return true;
+    if (r.status != 1) return false;
+    return fmaxf((float)r.fa, 1.0e-3f) < __expf((float)r.steps * h - off);
+}
 int lp_launch_render_repack(const TraceArgs &a, const RemapArgs &ra, const BinetConsts &c, const CamConsts &cam,
                             int src_dtype, uint32_t flags, cudaStream_t stream);
