@@ -70,6 +70,13 @@ extern "C" {
                                      FULL frame (row pitch = width*channels elements) and every pixel
                                      is stored at its frame row, instead of into a compact tile       */
 
+#define LP_RENDER_ROW_RUNS 32u     /* lp_render_frame_bands, 8-bit tiles: 32 x 1 warp tiles (96-byte runs, 16-byte
+                                     stores into whole 32-byte sectors) instead of 8 x 4 (24-byte runs, 8-byte
+                                     stores).  For frames assembled in ONE GPU's memory by many peers: at 8 GPUs
+                                     the root's NVLink ingress takes ~200 GB/s of 8-byte partial-sector stores
+                                     but > 600 GB/s of full sectors; with up to four writers the 8 x 4 tile's
+                                     better lane efficiency wins (3-4 %).  Same pixels either way             */
+
 /* ---- ray status codes (metrics.py:69, :125) ------------------------------ */
 #define LP_RAY_ESCAPED    1
 #define LP_RAY_CAPTURED (-1)

@@ -35,6 +35,7 @@ TRACE_FUSED = 1
 RENDER_STAGED_STORES = 8   # lp_render_frame: 16-byte staged pixel stores (peer-memory tiles)
 TRACE_REPACK = 2            # opt-in lane re-packing schedule (lp_repack.cu); the default is one ray per thread
 RENDER_OUT_FRAME_ROWS = 16  # interleaved-band tile stored at its frame rows (peer frames)
+RENDER_ROW_RUNS = 32        # 8-bit tiles in 32 x 1 warp tiles: full-sector runs for frames many peers store into (lightpath.h)
 TRACE_HYBRID = 4   # FMA loop + strict re-trace of the few rays that linger near the photon sphere (lightpath.h)
 
 _CHUNK_BYTES = 8 << 20          # staging granularity of large pageable arrays

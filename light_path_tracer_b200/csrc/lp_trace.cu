@@ -507,11 +507,11 @@ extern "C" int lp_render_frame_bands(const void *src, int32_t src_dtype, int32_t
         tile_h_pref = tile_h_env ? v : LP_RENDER_DEFAULT_TILE_H;
     }
     int th = tile_h_pref;
-    // Frame-addressed 8-bit tiles are the row bands of a multi-GPU frame, stored into another GPU's memory
-    // over NVLink (dist.PeerFrame): an 8 x 4 tile's runs are 24 bytes — 8-byte stores into partial 32-byte
-    // sectors, ~200 GB/s into the root at 8 GPUs (measured: config 4 at 0.447 ms against 0.31 of compute) —
-    // where a 32 x 1 tile's run is 96 bytes = three whole sectors in 16-byte stores, like the float32 tiles'.
-    if (!tile_h_env && frame_rows && band_rows > 0 && (src_dtype == LP_DTYPE_U8 || src_dtype == LP_DTYPE_U8_UNIT)) th = 1;
+    // LP_RENDER_ROW_RUNS: 8-bit row bands of a frame that MANY peers store into one GPU's memory over NVLink
+    // (dist.PeerFrame at more than four ranks).  An 8 x 4 tile's runs are 24 bytes — 8-byte stores into partial
+    // 32-byte sectors, ~200 GB/s into the root at 8 GPUs (measured: config 4 at 0.447 ms against 0.31 of compute)
+    // — where a 32 x 1 tile's run is 96 bytes = three whole sectors in 16-byte stores, like the float32 tiles'.
+    if (!tile_h_env && (flags & LP_RENDER_ROW_RUNS) && (src_dtype == LP_DTYPE_U8 || src_dtype == LP_DTYPE_U8_UNIT)) th = 1;
     while (th > 1 && (cam.width % (32 / th) != 0 || rows % th != 0)) th >>= 1;
     a.tile_h = th; a.tiles_x = cam.width / (32 / th);
     a.tile_shift = (th == 4) ? 2u : (th == 2) ? 1u : 0u;

@@ -230,6 +230,8 @@ class PeerFrame:
         else:
             self.rows, self.bands = row_tiles(self.height, self.world)[self.rank], None
         self.epoch = 0
+        # more than four writers saturate the root's NVLink ingress with the 8 x 4 tile's 8-byte stores (lightpath.h)
+        self._run_flag = 0 if self.world <= 4 else 32       # _device.RENDER_ROW_RUNS
 
     def begin(self):
         """Start frame epoch+1: returns (tile tensor in rank dst's buffer, (row0, n_rows), bands,
@@ -243,8 +245,8 @@ class PeerFrame:
         root = self.root[e % self.buffers]
         row0, rows = self.rows
         if self.bands is None:
-            return root[row0:row0 + rows], self.rows, None, dev.RENDER_STAGED_STORES
-        return root[row0:], self.rows, self.bands, dev.RENDER_STAGED_STORES | dev.RENDER_OUT_FRAME_ROWS
+            return root[row0:row0 + rows], self.rows, None, dev.RENDER_STAGED_STORES | self._run_flag
+        return root[row0:], self.rows, self.bands, dev.RENDER_STAGED_STORES | dev.RENDER_OUT_FRAME_ROWS | self._run_flag
 
     def complete(self):
         """Stream-ordered after this rank's render kernel: raise this rank's flag on dst; on dst,
