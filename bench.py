@@ -906,12 +906,12 @@ def single_gpu_records(args, torch, il, dev, metric, ext, timed, src8_host, fov,
 
 
 # FP64-pipe instructions per step attempt (per ray) of the two adaptive integrators as executed:
-#   RK45 — the equatorial four-component kernel lp_rk45_eq_kernel: ncu source counts (profiles/r2x_ncu_rk45.md,
-#          960x540 rays, 293.4 attempts per ray): 662 804 FP64 warp instructions per warp x 2 368 warps x 27.8
-#          active threads / 1.521e8 attempts = 287 (before the controller / right-hand-side trims of this round:
+#   RK45 — the equatorial four-component kernel lp_rk45_eq_kernel: ncu source counts (profiles/r2ab_ncu_rk45.md,
+#          960x540 rays, 293.4 attempts per ray): 667 330 FP64 warp instructions per warp x 2 368 warps x 27.8
+#          active threads / 1.521e8 attempts = 289 (before the controller / right-hand-side trims of this round:
 #          372; the eight-component kernel it replaced: 620);
 #   Kerr — 7 right-hand sides of 204 FP64 instructions + 370 of stage / error sums, from the SASS.
-RK45_FP64_SLOTS_PER_ATTEMPT = 287
+RK45_FP64_SLOTS_PER_ATTEMPT = 289
 KERR_FP64_SLOTS_PER_ATTEMPT = 1600
 
 

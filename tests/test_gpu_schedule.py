@@ -40,7 +40,10 @@ def test_interleaved_bands_equal_full_frame(native, dtype):
             tile = il.render_frame(src, fov, 30.0, metric, psi=(0.03, -0.02), rows=(row0, rows), bands=bands,
                                    unit_u8=u8)
             assert torch.equal(tile, full[idx])
-            for extra in (0, dev.RENDER_STAGED_STORES, dev.TRACE_REPACK, dev.TRACE_REPACK | dev.RENDER_STAGED_STORES):
+            # (RENDER_ROW_RUNS: the 32 x 1 warp tiles PeerFrame asks for when more than four ranks store 8-bit
+            # bands into the root — same pixels, and a no-op for float32)
+            for extra in (0, dev.RENDER_STAGED_STORES, dev.TRACE_REPACK, dev.TRACE_REPACK | dev.RENDER_STAGED_STORES,
+                          dev.RENDER_ROW_RUNS, dev.RENDER_ROW_RUNS | dev.RENDER_STAGED_STORES):
                 il.render_frame(src, fov, 30.0, metric, psi=(0.03, -0.02), rows=(row0, rows), bands=bands,
                                 unit_u8=u8, out=frame[row0:],
                                 flags=dev.TRACE_HYBRID | dev.RENDER_OUT_FRAME_ROWS | extra)
@@ -58,6 +61,9 @@ def test_staged_stores_u8(native):
             ref = il.render_frame(src, fov, 100.0, metric, unit_u8=unit)
             out = il.render_frame(src, fov, 100.0, metric, unit_u8=unit,
                                   flags=dev.TRACE_HYBRID | dev.RENDER_STAGED_STORES)
+            assert torch.equal(ref, out)
+            out = il.render_frame(src, fov, 100.0, metric, unit_u8=unit,
+                                  flags=dev.TRACE_HYBRID | dev.RENDER_STAGED_STORES | dev.RENDER_ROW_RUNS)
             assert torch.equal(ref, out)
             big = torch.full((H * W * 3 + 32,), 77, device="cuda", dtype=torch.uint8)
             for shift, rows in ((0, (7, H - 20)), (1, (0, H)), (16, (3, 50))):
