@@ -39,19 +39,20 @@ int lp_remap_try_tma(const RemapArgs &a, const CamConsts &cam, int src_dtype, in
 
 // sin and cos on [0, pi/2] (final_alpha of a sampled pixel is a float32 in that range): one
 // conditional reflection about pi/4 instead of a general quadrant reduction, the fdlibm kernel
-// polynomials with literal coefficients (compiler constant bank operands, nothing to load).
+// polynomials with their coefficients from the constant bank (c_sin_poly / c_cos_poly, lp_internal.cuh:
+// an FP64 instruction of sm_100 takes a constant through a uniform register, and a literal double costs two
+// UMOVs where a table entry costs half an LDCU.128).
+static __constant__ double c_quadrant[3] = {0.78539816339744828, 1.5707963267948966, 6.123233995736766e-17};   // pi/4, pi/2 hi, lo
 __device__ __forceinline__ void sincos_first_quadrant(double x, double &s, double &c)
 {
-    const bool hi = x > 0.78539816339744828;                     // pi/4
+    const bool hi = x > c_quadrant[0];
     // pi/2 - x with the low word of pi/2: exact enough for a float32-valued x
-    const double r = hi ? (1.5707963267948966 - x) + 6.123233995736766e-17 : x;
+    const double r = hi ? (c_quadrant[1] - x) + c_quadrant[2] : x;
     const double z = r * r;
-    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-    ps = fma(ps, z, 2.75573137070700676789e-06);   pc = fma(pc, z, -2.75573143513906633035e-07);
-    ps = fma(ps, z, -1.98412698298579493134e-04);  pc = fma(pc, z, 2.48015872894767294178e-05);
-    ps = fma(ps, z, 8.33333333332248946124e-03);   pc = fma(pc, z, -1.38888888888741095749e-03);
-    ps = fma(ps, z, -1.66666666666666324348e-01);  pc = fma(pc, z, 4.16666666666666019037e-02);
+    double ps = c_sin_poly[5];
+    double pc = c_cos_poly[5];
+#pragma unroll
+    for (int k = 4; k >= 0; --k) { ps = fma(ps, z, c_sin_poly[k]); pc = fma(pc, z, c_cos_poly[k]); }
     const double sr = fma(r * z, ps, r);
     const double cr = fma(z * z, pc, fma(-0.5, z, 1.0));
     s = hi ? cr : sr;
@@ -74,7 +75,8 @@ __device__ __forceinline__ void quad_offsets(const RemapArgs &a, const CamConsts
         const bool samp = fa[p] <= LP_HALF_PI_F32;               // false for NaN
         const double xc = cam_x(cam, col + p);
         const double A = fma(xc, cam.ex0, Ay), B = fma(xc, cam.ey0, By);
-        const double n2 = fmax(fma(A, A, B * B), 1e-300);        // the on-axis pixel itself is never sampled
+        const double n2r = fma(A, A, B * B);
+        const double n2 = (n2r > 1e-300) ? n2r : 1e-300;         // the on-axis pixel itself is never sampled (compare + select: fmax is ~7 instructions)
         const double inv = fast_rsqrt(n2);
         const double st = A * inv, ct = B * inv;
         double sf, cf;
@@ -120,6 +122,8 @@ __device__ __forceinline__ void quad_gather(const float *__restrict__ src, const
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
         if (off[p] >= 0) {
+            // (an 8-byte + 4-byte pair per texel instead of three 4-byte loads measured no faster: the kernel is
+            // bound neither by L1 wavefronts nor — after the constant-table trims — by the issue port)
             o[3 * p] = __ldg(src + off[p]);
             o[3 * p + 1] = __ldg(src + off[p] + 1);
             o[3 * p + 2] = __ldg(src + off[p] + 2);
