@@ -14,7 +14,13 @@
 #define LP_RENDER_DEFAULT_TILE_H 4
 #define LP_RENDER_DEFAULT_DYN 0
 #define LP_RENDER_DEFAULT_SPAN 2
-#define LP_TRACE_DEFAULT_BLOCK 64   /* rays per CTA; LP_TRACE_BLOCK=32|64|128|256 overrides (tuning) */
+#define LP_TRACE_DEFAULT_BLOCK 256  /* rays per CTA; LP_TRACE_BLOCK=32|64|128|256 overrides (tuning).  Measured on the
+                                       14-instruction kernel (profiles/r2af_knob_sweep*.log): 256 is 4 % faster than 64 at 4K
+                                       and 8K, 8-9 % on 1080p / divergent frames (with the 18-instruction step of the first
+                                       half of the round 64 and 128 were equal) */
+/* frames of fewer rays than this run two RK4 steps per trip instead of four (less speculation past the exit and a
+   smaller loop: 7 % faster at 1024 x 1024, 1 % at 4K r_obs = 15; four steps are 2.5-3.5 % faster at 4K / 8K r_obs = 100) */
+#define LP_RENDER_TRIP4_MIN_RAYS 4000000LL
 
 // LP_TRACE_HYBRID rule.  The FMA loop (scaled second-order form, lp_internal.cuh) differs from the strict one
 // by ~1e-16 per operation.  A perturbation d of the orbit obeys d'' = (-1 + 6 M u) d: it can only grow where
@@ -369,14 +375,15 @@ lp_render_kernel(const TraceArgs a, const RemapArgs ra, const BinetConsts c, con
 }
 
 // RK4 steps per loop trip of the fast path: LP_RENDER_TRIP=2|4 (tuning knob).
-static int render_trip()
+static int render_trip(long long n_rays)
 {
-    static int cached = 0;
-    if (!cached) {
+    static int cached = -1;
+    if (cached < 0) {
         const char *e = getenv("LP_RENDER_TRIP");
-        cached = (e && atoi(e) == 2) ? 2 : (e && atoi(e) == 4) ? 4 : LP_RENDER_DEFAULT_TRIP;
+        cached = (e && atoi(e) == 2) ? 2 : (e && atoi(e) == 4) ? 4 : 0;      // 0: by frame size
     }
-    return cached;
+    if (cached) return cached;
+    return n_rays >= LP_RENDER_TRIP4_MIN_RAYS ? 4 : 2;
 }
 
 // LP_RENDER_DYN=0|1 (tuning knob): ticket-drawing resident grid (see lp_render_kernel) or one CTA per
@@ -426,7 +433,7 @@ static int launch_render_mb(const TraceArgs &a_in, const RemapArgs &ra, const Bi
         const int span = render_span();
         const long long tickets = (warp_tiles + span - 1) / span;
         // (the ticket schedule is instantiated for the default arithmetic only: FMA loop, fast path, 4-step trips)
-        if (chunks > resident && tickets < 0x7fffffffLL - 0x100000 && fused && icmp && render_trip() == 4) {
+        if (chunks > resident && tickets < 0x7fffffffLL - 0x100000 && fused && icmp && render_trip(a.n) == 4) {
             static unsigned next_slot = 0;
             a.dyn_tickets = (int32_t)tickets; a.dyn_span = span;
             a.dyn_slot = (int32_t)(__atomic_fetch_add(&next_slot, 1u, __ATOMIC_RELAXED) % LP_TICKET_SLOTS);
@@ -438,11 +445,11 @@ static int launch_render_mb(const TraceArgs &a_in, const RemapArgs &ra, const Bi
         return lp_check_launch();
     }
     if (fused) {
-        if (icmp && render_trip() == 4) lp_render_kernel<true, true, T, MINB, 4><<<grid, block, 0, stream>>>(a, ra, c, cam);
+        if (icmp && render_trip(a.n) == 4) lp_render_kernel<true, true, T, MINB, 4><<<grid, block, 0, stream>>>(a, ra, c, cam);
         else if (icmp) lp_render_kernel<true, true, T, MINB, 2><<<grid, block, 0, stream>>>(a, ra, c, cam);
         else      lp_render_kernel<true, false, T, MINB, 2><<<grid, block, 0, stream>>>(a, ra, c, cam);
     } else {
-        if (icmp && render_trip() == 4) lp_render_kernel<false, true, T, MINB, 4><<<grid, block, 0, stream>>>(a, ra, c, cam);
+        if (icmp && render_trip(a.n) == 4) lp_render_kernel<false, true, T, MINB, 4><<<grid, block, 0, stream>>>(a, ra, c, cam);
         else if (icmp) lp_render_kernel<false, true, T, MINB, 2><<<grid, block, 0, stream>>>(a, ra, c, cam);
         else      lp_render_kernel<false, false, T, MINB, 2><<<grid, block, 0, stream>>>(a, ra, c, cam);
     }
