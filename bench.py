@@ -288,7 +288,9 @@ def fp64_roofline(kernel, flops, kern_ms, peak_tf, traffic, flop_model, executed
             "issue_port_frac": (2.0 * f64 + oth) * warps / (148 * 4) / cycles,
             "what": "fp64_pipe_frac = executed FP64 instructions x 2 flop / time / measured DFMA peak (FP64-pipe occupancy); "
                     "issue_port_frac = (2 x FP64 + other) warp instructions per SM sub-partition / elapsed cycles at "
-                    "%d MHz (an FP64 instruction holds the dispatch port for two cycles): the bound this kernel runs at" % sm_mhz,
+                    "%d MHz (an FP64 instruction holds the dispatch port for two cycles): the rate this kernel runs at — an "
+                    "empirical model, within a few per cent (ncu: issue active + FP64 pipe active / 2 = 101-104 %% of the "
+                    "cycles; a value slightly above 1 means some instructions issued in the shadow of an FP64 one)" % sm_mhz,
             "source": "%s (instruction counts; not re-measured in this run)" % executed["source"]}
     return out
 
