@@ -229,11 +229,10 @@ __device__ __forceinline__ void kerr_dp_stages(const double (&state)[5], const d
     kerr_rhs<EXACT>(nxt, p_t, p_phi, M, sp, r_floor, k7);
 }
 
-// Sum of squared scaled errors (metrics.py:505-513).  The five quotients e_i / scale_i are formed
-// with the branch-free division halves (bit-identical to `/` for finite operands, scale >= atol
-// > 0; a numerator below 2^-960 squares to zero either way), so the five dependent chains
-// interleave instead of each waiting behind its own slow-path branch; anything non-finite
-// takes the literal IEEE form.
+// Sum of squared scaled errors (metrics.py:505-513).  The five quotients e_i / scale_i go over a
+// straight-line reciprocal (a few ulp; scale >= atol > 0): the norm only feeds the step controller,
+// whose power is a few-ulp routine itself (inv_tenth_root), and an accept / reject decision could
+// only change for an error norm within ~1e-16 of 1.  Anything non-finite takes the literal IEEE form.
 __device__ __forceinline__ double kerr_err_sq(const double (&state)[5], const double (&nxt)[5],
                                               const double (&k1)[5], const double (&k3)[5], const double (&k4)[5],
                                               const double (&k5)[5], const double (&k6)[5], const double (&k7)[5],
@@ -243,12 +242,13 @@ __device__ __forceinline__ double kerr_err_sq(const double (&state)[5], const do
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
         e[i] = h * (kE1 * k1[i] + kE3 * k3[i] + kE4 * k4[i] + kE5 * k5[i] + kE6 * k6[i] + kE7 * k7[i]);
-        sc[i] = atol + rtol * fmax(fabs(state[i]), fabs(nxt[i]));
+        const double as = fabs(state[i]), an = fabs(nxt[i]);
+        sc[i] = atol + rtol * ((as > an) ? as : an);       // compare + select: fmax is ~7 instructions on sm_100
     }
     double err_sq = 0.0;
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
-        const double q = div_by(e[i], sc[i], div_rcp(sc[i]));
+        const double q = e[i] * fast_rcp(sc[i]);           // sc >= atol > 0; only the step controller sees the norm
         err_sq += q * q;
     }
     if (!isfinite(err_sq)) {
@@ -428,7 +428,7 @@ __device__ __forceinline__ void kerr_trip(double (&state)[5], double (&k1)[5], d
                 double pow_term = 0.9 * inv_tenth_root(e2);
                 if (!(err_sq == err_sq)) pow_term = err_sq;              // NaN stays NaN (fmin / fmax below drop it)
                 if (err_sq > 5.0) {                                      // err_norm > 1: reject, metrics.py:516-522
-                    const double factor = fmax(0.2, pow_term);
+                    const double factor = (pow_term > 0.2) ? pow_term : 0.2;        // max(0.2, .): NaN -> 0.2 like fmax
                     h *= factor;
                     if (h < h_min) done = 2;
                 } else {
@@ -455,7 +455,7 @@ __device__ __forceinline__ void kerr_trip(double (&state)[5], double (&k1)[5], d
                         } else if (e2 < 1e-20) {                        // err_norm < 1e-10
                             h *= 5.0;
                         } else {
-                            h *= fmin(5.0, pow_term);
+                            h *= (pow_term < 5.0) ? pow_term : 5.0;                 // min(5.0, .): NaN -> 5.0 like fmin
                         }
                     }
                 }
