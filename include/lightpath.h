@@ -43,8 +43,9 @@ extern "C" {
 /* ---- flags for the tracer entry points ---------------------------------- */
 #define LP_TRACE_STRICT     0u    /* default: every fp64 op separately rounded, in the
                                      reference's order (bit-identical u, w, phi)   */
-#define LP_TRACE_FUSED      1u    /* allow FMA contraction inside the RK4 step
-                                     (faster, ulp-level different trajectories)     */
+#define LP_TRACE_FUSED      1u    /* the same RK4 step in its second-order form, in the scaled
+                                     variable 3Mu, FMA-contracted: 14 instead of 34 FP64
+                                     instructions (ulp-level different trajectories)      */
 #define LP_TRACE_REPACK     2u    /* lp_render_frame: opt-in lane re-packing schedule (persistent
                                      warps; a lane whose ray has left the integration band hands it to
                                      the warp's result queue and takes the next prepared ray, so
