@@ -386,6 +386,15 @@ int lp_kerr_trace_alpha32(const float *alpha32, const lp_camera *h_cam, int32_t 
                           double lambda_max, float *out_fa32, uint16_t *out_w16,
                           int8_t *out_status, int32_t *out_steps, void *stream);
 
+/* ---- introspection ---------------------------------------------------------- */
+
+/* The LP_TRACE_HYBRID rule of one configuration (host arithmetic only, no device needed; csrc/lp_trace.cu):
+ * a ray of the FMA loop is re-traced strictly when steps > *steps_all, or when steps > *steps_none and
+ * max(final_alpha, 1e-3) < exp(steps * h_max - *exp_offset).  *phi_outside = the angle a critical ray sweeps
+ * outside r = 6M between r_obs and 2 r_obs (where rounding differences cannot grow).  Any output may be NULL. */
+int lp_hybrid_retrace_rule(double M, double r_obs, double h_max,
+                           int32_t *steps_all, int32_t *steps_none, double *exp_offset, double *phi_outside);
+
 /* ---- measurement helpers --------------------------------------------------- */
 
 /* FP64 pipe micro-benchmark: every thread runs `iters` rounds of 8 independent

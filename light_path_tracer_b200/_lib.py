@@ -78,6 +78,7 @@ SYMBOLS = {
     "lp_kerr_trace_alpha32": (ctypes.c_int, [_VP, _CAMP, _I32, _I32, _VP, _D, _D, _D, _D, _D, _D, _VP, _VP, _VP,
                                              _VP, _VP]),
     "lp_bench_dfma": (ctypes.c_int, [_I32, _I32, _I32, _VP, _VP]),
+    "lp_hybrid_retrace_rule": (ctypes.c_int, [_D, _D, _D, _VP, _VP, _VP, _VP]),
 }
 
 

@@ -84,6 +84,18 @@ void lp_hybrid_rule(uint32_t flags, double M, double r_obs, double h_max, TraceA
     a->retrace_off = (float)(LP_HYBRID_RETRACE_PHI + phi_out);
 }
 
+extern "C" int lp_hybrid_retrace_rule(double M, double r_obs, double h_max,
+                                      int32_t *steps_all, int32_t *steps_none, double *exp_offset, double *phi_outside)
+{
+    TraceArgs a = {};
+    lp_hybrid_rule(LP_TRACE_HYBRID, M, r_obs, h_max, &a);
+    if (steps_all) *steps_all = a.retrace_steps;
+    if (steps_none) *steps_none = a.retrace_steps_small;
+    if (exp_offset) *exp_offset = (double)a.retrace_off;
+    if (phi_outside) *phi_outside = hybrid_phi_outside(M, r_obs);
+    return LP_OK;
+}
+
 // One ray per thread, one CTA per `blockDim.x` consecutive rays.  The grid is NOT
 // persistent on purpose: the SMSP arbiter is unfair between always-eligible warps, so a
 // resident-forever grid finishes its warps at very different times and the tail runs

@@ -185,3 +185,39 @@ def test_fast_pixel_coordinates_are_exact(native):
         for n, f in ((W, cam.fx), (H, cam.fy)):
             x = np.arange(n) - n / 2
             assert np.all(np.isfinite(x / f))
+
+
+def test_hybrid_retrace_rule(native):
+    """LP_TRACE_HYBRID's re-trace rule (host arithmetic, csrc/lp_trace.cu): the angle a critical ray sweeps
+    outside r = 6M against an independent quadrature, and the thresholds that follow from it."""
+    import ctypes
+    lib = native.capi()
+
+    def rule(M, r_obs, h=0.05):
+        sa, sn = ctypes.c_int32(), ctypes.c_int32()
+        off, po = ctypes.c_double(), ctypes.c_double()
+        assert lib.lp_hybrid_retrace_rule(M, r_obs, h, ctypes.byref(sa), ctypes.byref(sn), ctypes.byref(off),
+                                          ctypes.byref(po)) == 0
+        return sa.value, sn.value, off.value, po.value
+
+    def phi_out_ref(M, r_obs):
+        u6 = 1.0 / (6 * M)
+        tot = 0.0
+        for u0 in (1.0 / r_obs, 0.5 / r_obs):
+            if u0 < u6:
+                u = np.linspace(u0, u6, 200001)
+                f = 1.0 / np.sqrt(1.0 / (27 * M * M) - u * u + 2 * M * u ** 3)
+                tot += float(np.sum((f[1:] + f[:-1]) * 0.5 * np.diff(u)))
+        return tot
+
+    for M, r_obs in ((1.0, 100.0), (1.0, 3.49), (1.0, 1000.0), (2.5, 40.0), (10.0, 6474.0), (1.0, 5.0), (1.0, 2.3)):
+        sa, sn, off, po = rule(M, r_obs)
+        ref = phi_out_ref(M, r_obs)
+        assert abs(po - ref) <= 1e-6 * max(ref, 1.0), (M, r_obs, po, ref)
+        assert abs(off - (11.5 + 0.95 * po)) < 1e-5
+        assert sa == int(np.floor((11.5 + 0.95 * po) / 0.05 + 1e-9)) and sn == int(np.floor((4.6 + 0.95 * po) / 0.05 + 1e-9))
+    # scale invariance (r_obs / M fixed), an observer inside 6M on the way in, and the step size
+    assert abs(rule(1.0, 100.0)[3] - rule(7.0, 700.0)[3]) < 1e-9
+    assert rule(1.0, 2.3)[3] == 0.0 and 0.0 < rule(1.0, 3.49)[3] < 0.2 and 1.8 < rule(1.0, 100.0)[3] < 1.9
+    po = rule(1.0, 100.0)[3]
+    assert rule(1.0, 100.0, 0.025)[0] == int(np.floor((11.5 + 0.95 * po) / 0.025 + 1e-9))

@@ -147,3 +147,29 @@ def test_rk45_kerr_golden_rays(oracle, golden):
         assert (r["outcome"], r["n_points"], r["nfev"], r["status"]) == (int(oc), int(npts), int(nfev), int(status)), i
         assert abs(r["t_final"] - tf) <= 1e-11 * max(1.0, tf)
         assert (np.abs(r["y_final"] - g["y_final"][i]) <= 1e-11 * np.maximum(np.abs(g["y_final"][i]), 1e-3)).all()
+
+
+def test_acos_restatement_accuracy(tmp_path):
+    """lp_acos_unit (csrc/lp_internal.cuh) stands in for np.arccos on the device.  tools/acos_study.c runs
+    the same operation sequence on the host (coefficient table tools/acos_coef.h, the MUFU seed modelled
+    as a ~20-bit reciprocal square root) against long double arithmetic: worst error below 0.75 ulp, and
+    the end points / NaN behave like the library's."""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "acos_study")
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", os.path.join(root, "tools", "acos_study.c"), "-lm", "-o", exe],
+                   check=True, cwd=os.path.join(root, "tools"))
+    out = subprocess.run([exe, "4000000"], check=True, capture_output=True, text=True).stdout
+    worst = float(re.search(r"worst mine=([0-9.]+) ulp", out).group(1))
+    assert worst < 0.75, out
+    lines = out.strip().splitlines()[1:]
+    for ln in lines:                                   # "x -> mine (libm ref)"
+        mine, ref = re.search(r"-> (\S+) \(libm (\S+)\)", ln).groups()
+        assert mine == ref, ln
+    # the device table is the same table
+    cuh = open(os.path.join(root, "light_path_tracer_b200", "csrc", "lp_internal.cuh")).read()
+    coef = open(os.path.join(root, "tools", "acos_coef.h")).read()
+    for c in re.findall(r"(-?0x1\.[0-9a-f]+p[-+]\d+)", coef):
+        assert c in cuh, c

@@ -45,10 +45,11 @@ static double ulp_err(double got, long double ref) {
     int ex; frexp(rd, &ex); long double u = ldexpl(1.0L, ex - 53);
     return (double)fabsl(((long double)got - ref) / u);
 }
-int main() {
+int main(int argc, char **argv) {
+    const long n_samples = argc > 1 ? atol(argv[1]) : 40000000;
     double worst = 0, worstg = 0, wx = 0; long ndiff = 0, n = 0;
     srand(1);
-    for (long i = 0; i < 40000000; i++) {
+    for (long i = 0; i < n_samples; i++) {
         double x;
         int m = i % 4;
         double u = (rand() + 0.5) / (RAND_MAX + 1.0), v = (rand() + 0.5) / (RAND_MAX + 1.0);
