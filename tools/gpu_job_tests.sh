@@ -1,2 +1,6 @@
+#!/bin/bash
+# the driver's own sequence on one GPU: GPU suite, smoke, bench line
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -q -m gpu -x > gpurun_out/r2_final_pytest_gpu.log 2>&1; echo "pytest gpu rc=$?"; tail -4 gpurun_out/r2_final_pytest_gpu.log
+timeout 1500 python -m pytest tests -q -m gpu -x > gpurun_out/r2_final_pytest_gpu.log 2>&1; echo "pytest gpu rc=$?"; tail -3 gpurun_out/r2_final_pytest_gpu.log
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_final_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/r2_final_smoke.log
+timeout 600 python bench.py > gpurun_out/r2_final_bench_n1.json 2> gpurun_out/r2_final_bench_n1.err; echo "bench rc=$?"; head -c 330 gpurun_out/r2_final_bench_n1.json; echo
