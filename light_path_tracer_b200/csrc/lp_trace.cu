@@ -1,7 +1,7 @@
 // lp_trace.cu — kernel (1a): one-thread-per-ray Schwarzschild Binet-equation RK4 tracer
 // (replaces metrics.py:49-145, :661-668 and the drivers at image_lens.py:133-178).
 //
-// Layout: one thread per ray, small CTAs (64 rays) back-filled by the hardware work
+// Layout: one thread per ray, non-persistent CTAs (256 rays) back-filled by the hardware work
 // distributor; a warp owns 32 consecutive rays (= 32 consecutive pixels of a row), so
 // the alpha loads and the fa / winding stores are fully coalesced.  The ray state
 // (u, w, step index) lives in registers in fp64; the per-configuration constants and the
@@ -99,7 +99,7 @@ extern "C" int lp_hybrid_retrace_rule(double M, double r_obs, double h_max,
 // One ray per thread, one CTA per `blockDim.x` consecutive rays.  The grid is NOT
 // persistent on purpose: the SMSP arbiter is unfair between always-eligible warps, so a
 // resident-forever grid finishes its warps at very different times and the tail runs
-// under-occupied (ncu, round 1: 5.6 of 8 warps active on average); small CTAs let the
+// under-occupied (ncu, round 1: 5.6 of 8 warps active on average); one-shot CTAs let the
 // hardware work distributor back-fill SMs as warps retire.
 template <bool FUSED, bool FAST, int SRC, bool WIDE>
 __global__ void __launch_bounds__(LP_TRACE_BLOCK)
