@@ -17,7 +17,8 @@
 #define LP_TRACE_DEFAULT_BLOCK 256  /* rays per CTA; LP_TRACE_BLOCK=32|64|128|256 overrides (tuning).  Measured on the
                                        14-instruction kernel (profiles/r2af_knob_sweep*.log): 256 is 4 % faster than 64 at 4K
                                        and 8K, 8-9 % on 1080p / divergent frames (with the 18-instruction step of the first
-                                       half of the round 64 and 128 were equal) */
+                                       half of the round 64 and 128 were equal; 512-thread CTAs are no faster than 256:
+                                       profiles/r2ak_block512.log) */
 /* frames of fewer rays than this run two RK4 steps per trip instead of four (less speculation past the exit and a
    smaller loop: 7 % faster at 1024 x 1024, 1 % at 4K r_obs = 15; four steps are 2.5-3.5 % faster at 4K / 8K r_obs = 100) */
 #define LP_RENDER_TRIP4_MIN_RAYS 4000000LL
